@@ -1,0 +1,152 @@
+/* vsb200.h -- C ABI of the B200-native dense video over-segmentation path.
+ *
+ * Drop-in boundary for the reference's DenseSegmentationUnit plug point
+ * (videosegmentation/video_segment @ c930c455; paths below are relative to the
+ * reference root).  The reference has no C ABI: these entry points are what a
+ * VideoUnit adapter binds.  Conventions mirror the reference:
+ *   - setup returns a status (<-> OpenStreams() bool + LOG(ERROR),
+ *     segmentation/segmentation_unit.cpp:58-116); 0 = ok;
+ *   - invariant violations abort (<-> CHECK);
+ *   - one handle is driven by one thread (<-> one thread per VideoUnit,
+ *     video_framework/video_pipeline.cpp:82-135);
+ *   - input buffers are HOST pointers owned by the caller and may be released as
+ *     soon as push returns; results are owned by the handle until the next pop.
+ * No torch / C++ types cross this boundary.  There is no CPU fallback: every
+ * entry point fails with VSB200_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ */
+#ifndef VSB200_H_
+#define VSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB200_OK 0
+#define VSB200_ERR_INVALID 1      /* bad argument / option (<-> OpenStreams false) */
+#define VSB200_ERR_NO_DEVICE 2    /* CUDA device missing or kernel image not loadable */
+#define VSB200_ERR_CUDA 3         /* CUDA runtime error (message via vsb200_last_error) */
+#define VSB200_ERR_EMPTY 4        /* pop with nothing ready */
+#define VSB200_ERR_UNSUPPORTED 5  /* option the reference has but this path does not build */
+
+/* Mirrors DenseSegmentationOptions (segmentation/dense_segmentation.h:42-95) plus the
+ * gflags that override it (segmentation/dense_segmentation.cpp:39-46,55-101). */
+typedef struct vsb200_dense_opts {
+  int32_t presmoothing;                  /* 0 none, 1 gaussian (unsupported), 2 bilateral (default) */
+  float frac_min_region_size;            /* 0.01 */
+  int32_t chunk_size;                    /* 20, >= 3 */
+  float chunk_overlap_ratio;             /* 0.2 */
+  int32_t num_constraint_frames;         /* 1 */
+  int32_t two_stage_oversegment;         /* 0 (1 unsupported) */
+  int32_t thin_structure_suppression;    /* 0 (1 unsupported: "does not work correctly" in the reference) */
+  int32_t enforce_n4_connectivity;       /* 1 */
+  int32_t enforce_spatial_connectedness; /* 1 */
+  int32_t color_distance;                /* 0 L1, 1 L2 (default) */
+  int32_t compute_vectorization;         /* 0 (1 unsupported) */
+  int32_t device;                        /* CUDA device ordinal */
+  int32_t want_id_maps;                  /* 1: every frame result also carries a host int32 id map */
+} vsb200_dense_opts;
+
+/* One frame's SegmentationDesc (segment_util/segmentation.proto:55-172) as flat arrays.
+ * Layout is shared with the oracle's vso_frame_result. */
+typedef struct vsb200_frame_result {
+  int32_t width, height, chunk_id, chunk_size, overlap_start, hierarchy_frame_idx;
+  int32_t connectedness;               /* 1 = N4_CONNECT, 2 = N8_CONNECT */
+  int32_t n_regions;
+  const int32_t* region_id;            /* [n_regions], Region2D.id */
+  const int32_t* interval_offset;      /* [n_regions + 1] into intervals */
+  const int32_t* intervals;            /* [3 * n_intervals]: y, left_x, right_x */
+  const float* shape_moments;          /* [6 * n_regions]: size mean_x mean_y xx xy yy */
+  int32_t n_compound;                  /* hierarchy level 0; > 0 only on the first frame of a chunk */
+  const int32_t* compound;             /* [4 * n_compound]: id size start_frame end_frame */
+  const int32_t* neighbor_offset;      /* [n_compound + 1] */
+  const int32_t* neighbor_id;          /* sorted ascending per region when ids are constrained */
+  int64_t pts;
+} vsb200_frame_result;
+
+typedef struct vsb200_dense vsb200_dense;
+
+/* Fills the reference defaults. */
+void vsb200_dense_default_opts(vsb200_dense_opts* o);
+/* Last error text of the calling thread ("" if none). */
+const char* vsb200_last_error(void);
+/* Number of usable sm_100 devices (0 if none); never throws. */
+int vsb200_device_count(void);
+
+/* ---- streaming engine: replaces DenseSegmentationUnit::OpenStreams / ProcessFrame /
+ *      PostProcess (segmentation/segmentation_unit.cpp:58-178) and everything below it
+ *      (DenseSegmentation::ProcessFrame, dense_segmentation.cpp:108-162). ---- */
+int vsb200_dense_create(const vsb200_dense_opts* o, int width, int height, int use_flow,
+                        vsb200_dense** out);
+/* One BGR24 frame (VideoFrame bytes, width_step = row_stride_bytes) and, when created with
+ * use_flow, the backward flow (interleaved float x,y; NULL on frame 0).  *n_ready = number of
+ * frames whose results became available (a whole chunk at a time). */
+int vsb200_dense_push(vsb200_dense*, const uint8_t* bgr, int row_stride_bytes,
+                      const float* flow_xy, int flow_row_stride_bytes, int64_t pts, int* n_ready);
+/* == ProcessFrame(flush = true) / PostProcess (segmentation_unit.cpp:154-161). */
+int vsb200_dense_flush(vsb200_dense*, int* n_ready);
+/* Results in input order. */
+int vsb200_dense_pop(vsb200_dense*, vsb200_frame_result* out);
+/* Host id map (int32 [height * width]) of the most recently popped frame, or NULL
+ * unless opts.want_id_maps. */
+const int32_t* vsb200_dense_last_id_map(vsb200_dense*);
+/* Serialises the most recently popped frame as a segmentation.SegmentationDesc protobuf
+ * message (proto2 wire format, segment_util/segmentation.proto:55-172).  Returns the
+ * byte count; copies at most cap bytes into buf. */
+size_t vsb200_dense_last_proto(vsb200_dense*, uint8_t* buf, size_t cap);
+/* Per-stage device/host milliseconds accumulated since creation:
+ * [0] h2d+preprocess [1] edge build [2] sort [3] merge [4] labels+n4+rle [5] host shaping
+ * [6] neighbours; and counters [7] kernels launched [8] merge rounds. */
+void vsb200_dense_stats(vsb200_dense*, double out[9]);
+void vsb200_dense_destroy(vsb200_dense*);
+
+/* Multi-GPU seam: region-id maps of the last two frames a group
+ * produced, to be injected into the successor group's first chunk exactly like
+ * overlap_segmentations_ (dense_segmentation.cpp:300-315).  Device pointers (int32 [h*w]),
+ * so the caller can ncclSend/ncclRecv them without staging. */
+int vsb200_dense_export_halo(vsb200_dense*, int32_t** dev_id_map_prev, int32_t** dev_id_map_last,
+                             int32_t* max_region_id);
+int vsb200_dense_import_halo(vsb200_dense*, const int32_t* dev_id_map_prev,
+                             const int32_t* dev_id_map_last, int32_t max_region_id);
+
+/* ---- kernel-level entry points (device pointers; used by the parity tests, bench.py and
+ *      the DenseSegGraphInterface adapter).  stream is a cudaStream_t (NULL = default). ---- */
+
+/* u8 BGR -> f32/255 (+ bilateral): DenseSegmentation::PreprocessFeatures
+ * (dense_segmentation.cpp:164-198), imagefilter::BilateralFilter (image_filter.cpp:184-277).
+ * scratch: >= vsb200_preprocess_scratch_bytes(). */
+size_t vsb200_preprocess_scratch_bytes(void);
+int vsb200_preprocess(const uint8_t* dev_bgr, int row_stride_bytes, int width, int height,
+                      int presmoothing, float* dev_out, void* dev_scratch, void* stream);
+/* Spatio-temporal edge weights of one frame: AddSpatialEdgesImpl + AddTemporal[Flow]EdgesImpl
+ * (dense_segmentation_graph.h:956-1142) with ColorDiff3L2 / L1 (pixel_distance.h:141-157).
+ * spatial_out: [h][w][4] (R, B, BL, BR); temporal_out: [h][w][9] (TL,T,TR,L,C,R,BL,B,BR about
+ * the flow-displaced clamped centre); missing edges hold -1.  prev / temporal_out / flow may
+ * be NULL (first frame of a chunk: spatial only). */
+int vsb200_edge_build(const float* dev_curr, const float* dev_prev, const float* dev_flow,
+                      int width, int height, int l1, float* dev_spatial_out,
+                      float* dev_temporal_out, void* stream);
+/* Bucket index of a weight, FastSegmentationGraph::AddEdge (segmentation_graph.h:158-162). */
+int vsb200_bucket_index(float weight);
+/* Stable bucket sort of the edge lists of one chunk graph (replaces the insert-time bucketing
+ * of segmentation_graph.h:158-162,367-374): keys are the 2048 weight buckets, order inside a
+ * bucket is (bucket list, anchor pixel, direction).  seg_ptrs[q] = device weights of bucket
+ * list q (NULL = absent), q even spatial ([h][w][4]), q odd temporal ([h][w][9]).
+ * codes_out: >= total valid edges uint32 edge codes ((q*N + pixel) << 4 | dir);
+ * bucket_start_out: device uint32/uint64 [2049]. */
+int vsb200_sort_edges(const float* const* host_seg_ptrs, int num_lists, int width, int height,
+                      uint32_t* dev_codes_out, uint64_t* dev_bucket_start_out, void* dev_scratch,
+                      size_t scratch_bytes, void* stream);
+size_t vsb200_sort_scratch_bytes(int num_lists, int width, int height);
+/* Whole-chunk over-segmentation of `slots` smoothed frames without constraints (graph build,
+ * sort, FastSegmentationGraph::SegmentGraph, segmentation_graph.h:339-463, flatten): writes the
+ * per-voxel region label (representative node id) to dev_labels_out [slots][h][w]. */
+int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slots, int l1,
+                         int min_region_size, int32_t* dev_labels_out, double* stats4, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VSB200_H_ */

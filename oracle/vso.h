@@ -1,0 +1,114 @@
+/* vso.h -- C ABI of the CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * The oracle is a dependency-free C++17 restatement of the reference's dense
+ * over-segmentation path (videosegmentation/video_segment @ c930c455).  Every
+ * function cites the reference file:line it follows (paths relative to the
+ * reference root).  PARITY UNPINNED: the reference ships no tests, golden
+ * vectors or fixtures for this path and cannot be built
+ * in this image (needs OpenCV 2.4 / FFmpeg 2.2 / glog / gflags / boost /
+ * protobuf), so this restatement is itself the pin.  Third-party arithmetic
+ * (cv::Mat::convertTo, cv::copyMakeBorder, cv::minMaxLoc) is cross-checked
+ * against Python cv2 by tests/golden/make_golden.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The product
+ * (video_segment_b200/) never links or imports it.
+ */
+#ifndef VSO_H_
+#define VSO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors DenseSegmentationOptions (segmentation/dense_segmentation.h:42-95). */
+typedef struct vso_dense_opts {
+  int32_t presmoothing;               /* 0 none, 1 gaussian(unsupported), 2 bilateral */
+  float frac_min_region_size;         /* 0.01 */
+  int32_t chunk_size;                 /* 20 */
+  float chunk_overlap_ratio;          /* 0.2 */
+  int32_t num_constraint_frames;      /* 1 */
+  int32_t enforce_n4_connectivity;    /* 1 */
+  int32_t enforce_spatial_connectedness; /* 1 */
+  int32_t color_distance;             /* 0 L1, 1 L2 */
+  int32_t num_threads;                /* oracle only: 1 = serial, >1 = reference-style
+                                         threading (thread per frame edge build,
+                                         row blocks for the bilateral filter) */
+} vso_dense_opts;
+
+/* Same layout as vsb200_frame_result (include/vsb200.h) so tests can compare
+ * the two field by field.  All pointers are owned by the handle and valid until
+ * the next pop / destroy. */
+typedef struct vso_frame_result {
+  int32_t width, height, chunk_id, chunk_size, overlap_start, hierarchy_frame_idx;
+  int32_t connectedness;              /* 1 = N4_CONNECT, 2 = N8_CONNECT */
+  int32_t n_regions;
+  const int32_t* region_id;           /* [n_regions] */
+  const int32_t* interval_offset;     /* [n_regions + 1] */
+  const int32_t* intervals;           /* [3 * n_intervals]: y, left_x, right_x */
+  const float* shape_moments;         /* [6 * n_regions]: size mean_x mean_y xx xy yy */
+  int32_t n_compound;                 /* > 0 only on the first frame of a chunk */
+  const int32_t* compound;            /* [4 * n_compound]: id size start_frame end_frame */
+  const int32_t* neighbor_offset;     /* [n_compound + 1] */
+  const int32_t* neighbor_id;
+  int64_t pts;
+} vso_frame_result;
+
+typedef struct vso_dense vso_dense;
+
+void vso_default_opts(vso_dense_opts* o);
+
+/* ---- stage functions (kernel-level oracles) ---- */
+
+/* cv::Mat::convertTo(CV_32FC3, 1/255)  -- dense_segmentation.cpp:180-181 */
+void vso_convert_u8_to_f32(const uint8_t* bgr, int w, int h, int row_stride, float* out);
+/* imagefilter::BilateralFilter(in, sigma_space, sigma_color) -- image_filter.cpp:184-277.
+ * lut_out (nullable) receives the 12288-entry exp LUT, scale_out the LUT scale. */
+void vso_bilateral(const float* in, int w, int h, float sigma_space, float sigma_color,
+                   float* out, int num_threads, float* lut_out, float* scale_out);
+/* Full PreprocessFeatures (dense_segmentation.cpp:164-198). */
+void vso_preprocess(const uint8_t* bgr, int w, int h, int row_stride, int presmoothing,
+                    float* out, int num_threads);
+/* Spatial edge weights in direction-planar layout out[d][y][x], d = R,B,BL,BR
+ * (dense_segmentation_graph.h:956-1000); missing edges hold -1. */
+void vso_spatial_weights(const float* img, int w, int h, int l1, float* out);
+/* Temporal edge weights out[d][y][x], d = TL,T,TR,L,C,R,BL,B,BR relative to the
+ * (flow displaced, clamped) centre in prev (dense_segmentation_graph.h:1002-1142);
+ * flow nullable; missing edges hold -1. */
+void vso_temporal_weights(const float* curr, const float* prev, const float* flow,
+                          int w, int h, int l1, float* out);
+/* Bucket index (segmentation_graph.h:158-162,336). */
+int vso_bucket_index(float weight);
+
+/* ---- streaming engine = DenseSegmentation (dense_segmentation.cpp) ---- */
+int vso_dense_create(const vso_dense_opts* o, int w, int h, int use_flow, vso_dense** out);
+int vso_dense_push(vso_dense*, const uint8_t* bgr, int row_stride, const float* flow_xy,
+                   int flow_row_stride_bytes, int64_t pts, int* n_ready);
+int vso_dense_flush(vso_dense*, int* n_ready);
+int vso_dense_pop(vso_dense*, vso_frame_result* out);
+void vso_dense_destroy(vso_dense*);
+
+/* Debug taps on the most recently segmented chunk (valid until next chunk):
+ * number of graph slots, per-node union-find labels right after SegmentGraph +
+ * FlattenUnionFind (before N4 / connectedness), and the per-slot id images after
+ * EnforceN4Connectivity.  Labels are reference representative ids (opaque). */
+int vso_dense_last_chunk_slots(vso_dense*);
+const int32_t* vso_dense_last_chunk_node_labels(vso_dense*);   /* [slots * w * h] */
+const int32_t* vso_dense_last_chunk_id_images(vso_dense*);     /* [slots * w * h], -1 on virtual slots */
+/* Merge statistics of the last chunk: regular, small-region, forced merges. */
+void vso_dense_last_chunk_merge_stats(vso_dense*, int64_t stats[3]);
+/* Stage wall-times accumulated since creation, seconds:
+ * [0] preprocess [1] edge build [2] segment graph [3] obtain results [4] shaping */
+void vso_dense_stage_seconds(vso_dense*, double out[5]);
+
+/* ---- whole-graph helper for merge-kernel parity: segment one chunk given the
+ * smoothed float frames (no constraints) and return node labels. ---- */
+int vso_segment_chunk_labels(const float* frames, int w, int h, int t, int l1,
+                             int min_region_size, int32_t* labels_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VSO_H_ */

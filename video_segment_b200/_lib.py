@@ -1,0 +1,97 @@
+"""ctypes loader of the in-tree CUDA library (libvsb200.so).  Fails loudly when the
+library is missing or cannot be loaded -- there is no CPU or PyTorch fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvsb200.so")
+
+
+class DenseOpts(C.Structure):
+    """vsb200_dense_opts (include/vsb200.h) == DenseSegmentationOptions
+    (reference segmentation/dense_segmentation.h:42-95)."""
+    _fields_ = [
+        ("presmoothing", C.c_int32), ("frac_min_region_size", C.c_float),
+        ("chunk_size", C.c_int32), ("chunk_overlap_ratio", C.c_float),
+        ("num_constraint_frames", C.c_int32), ("two_stage_oversegment", C.c_int32),
+        ("thin_structure_suppression", C.c_int32), ("enforce_n4_connectivity", C.c_int32),
+        ("enforce_spatial_connectedness", C.c_int32), ("color_distance", C.c_int32),
+        ("compute_vectorization", C.c_int32), ("device", C.c_int32), ("want_id_maps", C.c_int32),
+    ]
+
+
+class FrameResult(C.Structure):
+    """vsb200_frame_result (include/vsb200.h)."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("chunk_id", C.c_int32),
+        ("chunk_size", C.c_int32), ("overlap_start", C.c_int32),
+        ("hierarchy_frame_idx", C.c_int32), ("connectedness", C.c_int32),
+        ("n_regions", C.c_int32),
+        ("region_id", C.POINTER(C.c_int32)), ("interval_offset", C.POINTER(C.c_int32)),
+        ("intervals", C.POINTER(C.c_int32)), ("shape_moments", C.POINTER(C.c_float)),
+        ("n_compound", C.c_int32),
+        ("compound", C.POINTER(C.c_int32)), ("neighbor_offset", C.POINTER(C.c_int32)),
+        ("neighbor_id", C.POINTER(C.c_int32)),
+        ("pts", C.c_int64),
+    ]
+
+
+# every symbol include/vsb200.h declares
+EXPORTED_SYMBOLS = [
+    "vsb200_dense_default_opts", "vsb200_last_error", "vsb200_device_count",
+    "vsb200_dense_create", "vsb200_dense_push", "vsb200_dense_flush", "vsb200_dense_pop",
+    "vsb200_dense_last_id_map", "vsb200_dense_last_proto", "vsb200_dense_stats",
+    "vsb200_dense_destroy", "vsb200_dense_export_halo", "vsb200_dense_import_halo",
+    "vsb200_preprocess_scratch_bytes", "vsb200_preprocess", "vsb200_edge_build",
+    "vsb200_bucket_index", "vsb200_sort_edges", "vsb200_sort_scratch_bytes", "vsb200_segment_chunk",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libvsb200.so; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m video_segment_b200.build` "
+            "(nvcc, sm_100a).  This package has no CPU / PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.vsb200_last_error.restype = C.c_char_p
+    L.vsb200_device_count.restype = C.c_int
+    L.vsb200_dense_default_opts.argtypes = [C.POINTER(DenseOpts)]
+    L.vsb200_preprocess_scratch_bytes.restype = C.c_size_t
+    L.vsb200_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.vsb200_edge_build.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.vsb200_bucket_index.argtypes = [C.c_float]
+    L.vsb200_bucket_index.restype = C.c_int
+    L.vsb200_sort_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.vsb200_sort_scratch_bytes.restype = C.c_size_t
+    L.vsb200_sort_edges.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]
+    L.vsb200_segment_chunk.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                                       C.POINTER(C.c_double), vp]
+    L.vsb200_dense_create.argtypes = [C.POINTER(DenseOpts), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.vsb200_dense_push.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)]
+    L.vsb200_dense_flush.argtypes = [vp, C.POINTER(C.c_int)]
+    L.vsb200_dense_pop.argtypes = [vp, C.POINTER(FrameResult)]
+    L.vsb200_dense_last_id_map.argtypes = [vp]
+    L.vsb200_dense_last_id_map.restype = C.POINTER(C.c_int32)
+    L.vsb200_dense_last_proto.argtypes = [vp, vp, C.c_size_t]
+    L.vsb200_dense_last_proto.restype = C.c_size_t
+    L.vsb200_dense_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    L.vsb200_dense_destroy.argtypes = [vp]
+    L.vsb200_dense_export_halo.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32)]
+    L.vsb200_dense_import_halo.argtypes = [vp, vp, vp, C.c_int32]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vsb200_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")

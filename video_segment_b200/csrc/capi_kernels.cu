@@ -1,0 +1,187 @@
+// capi_kernels.cu -- kernel-level C-ABI entry points (include/vsb200.h) and the one-shot
+// whole-chunk segmentation used by the merge parity tests and bench.py.
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/vsb200.h"
+#include "common.cuh"
+#include "results.cuh"
+
+using namespace vsb;
+
+extern "C" {
+
+const char* vsb200_last_error(void) { return vsb::last_error(); }
+
+int vsb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+  }
+  return ok;
+}
+
+static int require_device() {
+  if (vsb200_device_count() <= 0) {
+    set_error("no sm_100 CUDA device available: this path has no CPU fallback");
+    return VSB200_ERR_NO_DEVICE;
+  }
+  return 0;
+}
+
+size_t vsb200_preprocess_scratch_bytes(void) { return preprocess_scratch_bytes(); }
+
+int vsb200_preprocess(const uint8_t* dev_bgr, int row_stride_bytes, int width, int height, int presmoothing,
+                      float* dev_out, void* dev_scratch, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!dev_bgr || !dev_out || !dev_scratch || width < 2 || height < 2 || row_stride_bytes < width * 3) {
+    set_error("vsb200_preprocess: bad arguments");
+    return VSB200_ERR_INVALID;
+  }
+  return launch_preprocess(dev_bgr, row_stride_bytes, width, height, presmoothing, dev_out, dev_scratch,
+                           (cudaStream_t)stream);
+}
+
+int vsb200_edge_build(const float* dev_curr, const float* dev_prev, const float* dev_flow, int width, int height,
+                      int l1, float* dev_spatial_out, float* dev_temporal_out, void* stream) {
+  if (int rc = require_device()) return rc;
+  return launch_edge_build(dev_curr, dev_prev, dev_flow, width, height, l1 != 0, dev_spatial_out, dev_temporal_out,
+                           (cudaStream_t)stream);
+}
+
+int vsb200_bucket_index(float weight) { return bucket_of(weight); }
+
+size_t vsb200_sort_scratch_bytes(int num_lists, int width, int height) {
+  return sort_scratch_bytes(num_lists, width, height);
+}
+
+int vsb200_sort_edges(const float* const* host_seg_ptrs, int num_lists, int width, int height,
+                      uint32_t* dev_codes_out, uint64_t* dev_bucket_start_out, void* dev_scratch,
+                      size_t scratch_bytes, void* stream) {
+  if (int rc = require_device()) return rc;
+  return launch_sort_edges(host_seg_ptrs, num_lists, width, height, dev_codes_out,
+                           (unsigned long long*)dev_bucket_start_out, dev_scratch, scratch_bytes,
+                           (cudaStream_t)stream);
+}
+
+// One chunk, no constraints: frames -> node labels.  Allocates and frees its own workspace
+// (a convenience entry point for tests / benchmarks; the streaming engine keeps its workspace).
+int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slots, int l1, int min_region_size,
+                         int32_t* dev_labels_out, double* stats4, void* stream) {
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)width * height, nodes = n * slots;
+  const int num_lists = 2 * slots - 1;
+  std::vector<void*> allocs;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    allocs.push_back(p);
+    return p;
+  };
+  auto cleanup = [&]() { for (void* p : allocs) cudaFree(p); };
+  int rc = 0;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) cudaEventCreate(&e);
+  do {
+    std::vector<const float*> seg(num_lists, nullptr);
+    size_t total_elems = 0;
+    bool oom = false;
+    for (int q = 0; q < num_lists; ++q) {
+      const size_t e = n * ((q & 1) ? 9 : 4);
+      float* p = (float*)dalloc(e * sizeof(float));
+      if (!p) { oom = true; break; }
+      seg[q] = p;
+      total_elems += e;
+    }
+    if (oom) { set_error("segment_chunk: out of device memory"); rc = VSB200_ERR_CUDA; break; }
+    uint32_t* codes = (uint32_t*)dalloc(total_elems * sizeof(uint32_t));
+    unsigned long long* bstart = (unsigned long long*)dalloc(sizeof(unsigned long long) * (kNumBuckets + 1));
+    const size_t sort_sc = sort_scratch_bytes(num_lists, width, height);
+    void* sort_scratch = dalloc(sort_sc);
+    int* parent = (int*)dalloc(nodes * sizeof(int));
+    RegionRec* rec = (RegionRec*)dalloc(nodes * sizeof(RegionRec));
+    if (!codes || !bstart || !sort_scratch || !parent || !rec) { set_error("segment_chunk: out of device memory"); rc = VSB200_ERR_CUDA; break; }
+    cudaEventRecord(ev[0], s);
+    for (int k = 0; k < slots && rc == 0; ++k) {
+      const float* cur = dev_frames + (size_t)k * n * 3;
+      rc = launch_init_nodes(cur, nullptr, k, width, height, parent, rec, s);
+      if (rc) break;
+      rc = launch_edge_build(cur, k ? cur - n * 3 : nullptr, nullptr, width, height, l1 != 0,
+                             (float*)seg[2 * k], k ? (float*)seg[2 * k - 1] : nullptr, s);
+    }
+    if (rc) break;
+    cudaEventRecord(ev[1], s);
+    rc = launch_sort_edges(seg.data(), num_lists, width, height, codes, bstart, sort_scratch, sort_sc, s);
+    if (rc) break;
+    cudaEventRecord(ev[2], s);
+    unsigned long long h_bstart[kNumBuckets + 1];
+    if (cudaMemcpyAsync(h_bstart, bstart, sizeof(h_bstart), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("segment_chunk: sort failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = VSB200_ERR_CUDA;
+      break;
+    }
+    unsigned long long max_bucket = 1;
+    for (int b = 0; b < kNumBuckets; ++b) max_bucket = std::max(max_bucket, h_bstart[b + 1] - h_bstart[b]);
+    // the weight lists are no longer needed: free them before the merge workspace is allocated
+    for (int q = 0; q < num_lists; ++q) {
+      cudaFree((void*)seg[q]);
+      allocs.erase(std::find(allocs.begin(), allocs.end(), (void*)seg[q]));
+    }
+    MergeParams mp;
+    mp.w = width; mp.h = height; mp.slots = slots; mp.min_region_size = min_region_size;
+    mp.force_merge_weight = l1 ? 0.002f : 0.001f;
+    mp.has_constraints = 0;
+    mp.flows = nullptr;
+    mp.codes = codes;
+    mp.bucket_start = bstart;
+    mp.parent = parent;
+    mp.rec = rec;
+    mp.res = (unsigned long long*)dalloc(nodes * 8);
+    mp.acc = (unsigned long long*)dalloc(nodes * 32);
+    mp.cl = (int*)dalloc(nodes * 4);
+    mp.hull = (int*)dalloc(nodes * 32);
+    mp.live_a = (uint32_t*)dalloc(max_bucket * 16);
+    mp.live_b = (uint32_t*)dalloc(max_bucket * 16);
+    mp.live_cap = max_bucket;
+    mp.counters = (unsigned long long*)dalloc(16 * 8);
+    mp.stats = mp.counters ? mp.counters + 8 : nullptr;
+    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.counters) {
+      set_error("segment_chunk: out of device memory (merge workspace)");
+      rc = VSB200_ERR_CUDA;
+      break;
+    }
+    cudaMemsetAsync(mp.res, 0xff, nodes * 8, s);
+    cudaMemsetAsync(mp.acc, 0, nodes * 32, s);
+    cudaMemsetAsync(mp.counters, 0, 16 * 8, s);
+    if ((rc = launch_init_iota(mp.cl, (long long)nodes, s))) break;
+    if ((rc = launch_init_hull(mp.hull, (long long)nodes, s))) break;
+    if ((rc = launch_merge(mp, s))) break;
+    cudaEventRecord(ev[3], s);
+    if ((rc = launch_flatten(parent, nullptr, dev_labels_out, (long long)nodes, s))) break;
+    unsigned long long h_stats[8];
+    if (cudaMemcpyAsync(h_stats, mp.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("segment_chunk: merge failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = VSB200_ERR_CUDA;
+      break;
+    }
+    if (stats4) {
+      float ms;
+      cudaEventElapsedTime(&ms, ev[0], ev[1]); stats4[0] = ms;   // init + edge build
+      cudaEventElapsedTime(&ms, ev[1], ev[2]); stats4[1] = ms;   // sort
+      cudaEventElapsedTime(&ms, ev[2], ev[3]); stats4[2] = ms;   // merge (incl. workspace init)
+      stats4[3] = (double)h_stats[0];                            // merge rounds
+    }
+  } while (0);
+  for (auto& e : ev) cudaEventDestroy(e);
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

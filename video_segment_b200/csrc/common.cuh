@@ -1,0 +1,97 @@
+// common.cuh -- shared declarations of the sm_100a dense over-segmentation kernels.
+// All arithmetic that feeds parity (pixel conversion, bilateral weights, edge
+// weights, descriptor means) is compiled with -fmad=false so that every float
+// operation rounds exactly like the reference's scalar x86-64 code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace vsb {
+
+constexpr int kNumBuckets = 2048;           // segmentation/dense_segmentation_graph.h:303
+constexpr int kLutBins = (1 << 12) * 3;     // imagefilter/image_filter.cpp:237
+constexpr int kBilateralRadius = 4;         // int(3.0f * 1.5f), image_filter.cpp:201
+constexpr int kBilateralTaps = 49;          // i*i + j*j <= 16
+
+// thread-local last error text, set by the launch wrappers
+void set_error(const char* fmt, ...);
+
+#define VSB_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::vsb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 3;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+// Bucket index, FastSegmentationGraph::AddEdge (segmentation/segmentation_graph.h:158-162)
+// with scale_ = 2048 / (1.0f + 1e-6f) (segmentation_graph.h:336).
+__host__ __device__ inline float bucket_scale() { return 2048 / (1.0f + 1e-6f); }
+__host__ __device__ inline int bucket_of(float w) {
+  const float v = w * bucket_scale();
+  return (int)(v < 2048.f ? v : 2048.f);
+}
+
+// Edge code: ((list * N + pixel) << 4) | dir.  list = reference bucket-list index
+// (2*slot spatial, 2*slot-1 temporal; dense_segmentation_graph.h:962,1077).
+__host__ __device__ inline uint32_t edge_code(int list, int n_pix, int pixel, int dir) {
+  return (((uint32_t)list * (uint32_t)n_pix + (uint32_t)pixel) << 4) | (uint32_t)dir;
+}
+
+// ---------------- launch wrappers (host) ----------------
+// preprocess.cu
+size_t preprocess_scratch_bytes();
+int launch_preprocess(const uint8_t* bgr, int stride, int w, int h, int presmoothing, float* out,
+                      void* scratch, cudaStream_t s);
+// edges.cu
+int launch_edge_build(const float* curr, const float* prev, const float* flow, int w, int h, bool l1,
+                      float* spatial, float* temporal, cudaStream_t s);
+// sort.cu
+size_t sort_scratch_bytes(int num_lists, int w, int h);
+int launch_sort_edges(const float* const* seg_ptrs, int num_lists, int w, int h, uint32_t* codes,
+                      unsigned long long* bucket_start, void* scratch, size_t scratch_bytes,
+                      cudaStream_t s);
+
+// merge.cu : region record, 32 bytes (one sector per root access)
+struct __align__(32) RegionRec {
+  int sz;            // voxels
+  int con;           // constraint id, -1 = unconstrained
+  float d0, d1, d2;  // mean colour descriptor (ColorMeanDescriptorTraits)
+  int fin;           // region_finalized
+  int pad0, pad1;
+};
+
+struct MergeParams {
+  int w, h, slots;                 // graph geometry; nodes = slots * w * h
+  int min_region_size;
+  float force_merge_weight;        // 0.001f (L2) / 0.002f (L1), dense_segmentation.cpp:259-264
+  int has_constraints;             // chunk > 0
+  const float* flows;              // optional [slots][h][w][2] (slot 0 unused), nullable
+  const uint32_t* codes;           // sorted edge codes
+  const unsigned long long* bucket_start;   // [2049]
+  int* parent;                     // [nodes]
+  RegionRec* rec;                  // [nodes]
+  unsigned long long* res;         // [nodes] epoch-tagged reservations
+  unsigned long long* acc;         // [nodes][4] fixed-point accumulators: sz, d0, d1, d2
+  int* cl;                         // [nodes] scratch cluster union-find
+  int* hull;                       // [nodes][8]: min0..2, max0..2, flags, conmin (float bits as int)
+  uint32_t* live_a;                // live edge buffers: triples (code, ru, rv)
+  uint32_t* live_b;
+  unsigned long long live_cap;     // in triples
+  unsigned long long* counters;    // [8] device counters
+  unsigned long long* stats;       // [8] rounds, commits, safe merges, ...
+};
+size_t merge_scratch_bytes(int w, int h, int slots, unsigned long long max_bucket_edges);
+int launch_merge(const MergeParams& p, cudaStream_t s);
+int launch_init_nodes(const float* frame, const int* constraint_ids, int slot, int w, int h, int* parent,
+                      RegionRec* rec, cudaStream_t s);
+int launch_init_virtual_nodes(const int* constraint_ids, int slot, int w, int h, int* parent, RegionRec* rec,
+                              int* first_of_id, int max_id, cudaStream_t s);
+
+// results.cu
+int launch_flatten(const int* parent_in, int* unused, int* labels, long long n, cudaStream_t s);
+const char* last_error();
+
+}  // namespace vsb
