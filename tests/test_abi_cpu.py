@@ -1,0 +1,63 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/vsb200.h
+declares; without a GPU the product refuses to run (no CPU fallback); host-side unit logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from video_segment_b200._lib import EXPORTED_SYMBOLS, LIB_PATH, lib
+    hdr = open(os.path.join(ROOT, "include", "vsb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(vsb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    assert sorted(EXPORTED_SYMBOLS) == declared
+    L = lib()
+    raw = C.CDLL(LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert L.vsb200_bucket_index(0.0) == 0 and L.vsb200_bucket_index(1.0) == 2047 and L.vsb200_bucket_index(1e10) == 2048
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from video_segment_b200._lib import lib
+    from video_segment_b200.unit import DenseSegmentationUnit
+    assert lib().vsb200_device_count() == 0
+    u = DenseSegmentationUnit()
+    assert not u.open_streams(64, 48)          # fails loudly (status + message), never computes on the CPU
+    assert b"no CPU fallback" in lib().vsb200_last_error()
+    with pytest.raises(RuntimeError):
+        u.process_frame(np.zeros((48, 64, 3), np.uint8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "video_segment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle_binding" not in txt and "libvso" not in txt and "vso.h" not in txt, f
+
+
+def test_default_opts_match_reference_defaults():
+    from video_segment_b200._lib import DenseOpts, lib
+    o = DenseOpts()
+    lib().vsb200_dense_default_opts(C.byref(o))
+    assert (o.presmoothing, o.chunk_size, o.num_constraint_frames) == (2, 20, 1)
+    assert abs(o.frac_min_region_size - 0.01) < 1e-9 and abs(o.chunk_overlap_ratio - 0.2) < 1e-7
+    assert (o.enforce_n4_connectivity, o.enforce_spatial_connectedness, o.color_distance) == (1, 1, 1)
+
+
+def test_synth_is_deterministic():
+    from video_segment_b200.synth import synth_clip
+    a = synth_clip(3, 80, 60, 3)
+    b = synth_clip(3, 80, 60, 3)
+    assert np.array_equal(a, b) and a.dtype == np.uint8 and a.shape == (3, 60, 80, 3)
+    assert not np.array_equal(a[0], a[1])

@@ -62,31 +62,40 @@ def lib() -> C.CDLL:
             "(nvcc, sm_100a).  This package has no CPU / PyTorch fallback.")
     L = C.CDLL(LIB_PATH)
     vp = C.c_void_p
-    L.vsb200_last_error.restype = C.c_char_p
-    L.vsb200_device_count.restype = C.c_int
-    L.vsb200_dense_default_opts.argtypes = [C.POINTER(DenseOpts)]
-    L.vsb200_preprocess_scratch_bytes.restype = C.c_size_t
-    L.vsb200_preprocess.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
-    L.vsb200_edge_build.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
-    L.vsb200_bucket_index.argtypes = [C.c_float]
-    L.vsb200_bucket_index.restype = C.c_int
-    L.vsb200_sort_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
-    L.vsb200_sort_scratch_bytes.restype = C.c_size_t
-    L.vsb200_sort_edges.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]
-    L.vsb200_segment_chunk.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp,
-                                       C.POINTER(C.c_double), vp]
-    L.vsb200_dense_create.argtypes = [C.POINTER(DenseOpts), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
-    L.vsb200_dense_push.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)]
-    L.vsb200_dense_flush.argtypes = [vp, C.POINTER(C.c_int)]
-    L.vsb200_dense_pop.argtypes = [vp, C.POINTER(FrameResult)]
-    L.vsb200_dense_last_id_map.argtypes = [vp]
-    L.vsb200_dense_last_id_map.restype = C.POINTER(C.c_int32)
-    L.vsb200_dense_last_proto.argtypes = [vp, vp, C.c_size_t]
-    L.vsb200_dense_last_proto.restype = C.c_size_t
-    L.vsb200_dense_stats.argtypes = [vp, C.POINTER(C.c_double)]
-    L.vsb200_dense_destroy.argtypes = [vp]
-    L.vsb200_dense_export_halo.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32)]
-    L.vsb200_dense_import_halo.argtypes = [vp, vp, vp, C.c_int32]
+    sigs = {
+        "vsb200_last_error": (None, C.c_char_p),
+        "vsb200_device_count": (None, C.c_int),
+        "vsb200_dense_default_opts": ([C.POINTER(DenseOpts)], None),
+        "vsb200_preprocess_scratch_bytes": (None, C.c_size_t),
+        "vsb200_preprocess": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp], C.c_int),
+        "vsb200_edge_build": ([vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp], C.c_int),
+        "vsb200_bucket_index": ([C.c_float], C.c_int),
+        "vsb200_sort_scratch_bytes": ([C.c_int, C.c_int, C.c_int], C.c_size_t),
+        "vsb200_sort_edges": ([C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp], C.c_int),
+        "vsb200_segment_chunk": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_double), vp], C.c_int),
+        "vsb200_dense_create": ([C.POINTER(DenseOpts), C.c_int, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
+        "vsb200_dense_push": ([vp, vp, C.c_int, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)], C.c_int),
+        "vsb200_dense_flush": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "vsb200_dense_pop": ([vp, C.POINTER(FrameResult)], C.c_int),
+        "vsb200_dense_last_id_map": ([vp], C.POINTER(C.c_int32)),
+        "vsb200_dense_last_proto": ([vp, vp, C.c_size_t], C.c_size_t),
+        "vsb200_dense_stats": ([vp, C.POINTER(C.c_double)], None),
+        "vsb200_dense_destroy": ([vp], None),
+        "vsb200_dense_export_halo": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32)], C.c_int),
+        "vsb200_dense_import_halo": ([vp, vp, vp, C.c_int32], C.c_int),
+    }
+    missing = []
+    for name, (argtypes, restype) in sigs.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        if argtypes is not None:
+            fn.argtypes = argtypes
+        fn.restype = restype
+    if missing and not os.environ.get("VSB200_ALLOW_PARTIAL_LIB"):
+        raise RuntimeError(f"{LIB_PATH} does not export {missing}: stale build, rebuild it")
     _lib = L
     return L
 

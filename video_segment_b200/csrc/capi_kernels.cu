@@ -1,6 +1,7 @@
 // capi_kernels.cu -- kernel-level C-ABI entry points (include/vsb200.h) and the one-shot
 // whole-chunk segmentation used by the merge parity tests and bench.py.
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -26,7 +27,9 @@ int vsb200_device_count(void) {
 }
 
 static int require_device() {
-  if (vsb200_device_count() <= 0) {
+  static int cached = -1;                       // device enumeration is slow (cudaGetDeviceProperties)
+  if (cached < 0) cached = vsb200_device_count();
+  if (cached <= 0) {
     set_error("no sm_100 CUDA device available: this path has no CPU fallback");
     return VSB200_ERR_NO_DEVICE;
   }
@@ -151,6 +154,8 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.live_cap = max_bucket;
     mp.counters = (unsigned long long*)dalloc(16 * 8);
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
+    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc(kNumBuckets * 4 * 8) : nullptr;
+    if (mp.debug) cudaMemsetAsync(mp.debug, 0, kNumBuckets * 4 * 8, s);
     if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.counters) {
       set_error("segment_chunk: out of device memory (merge workspace)");
       rc = VSB200_ERR_CUDA;
@@ -170,6 +175,21 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
       set_error("segment_chunk: merge failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = VSB200_ERR_CUDA;
       break;
+    }
+    if (mp.debug) {
+      std::vector<unsigned long long> dbg(kNumBuckets * 4);
+      cudaMemcpy(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost);
+      FILE* f = fopen(getenv("VSB200_MERGE_DEBUG"), "w");
+      if (f) {
+        unsigned long long prev = 0;
+        for (int b = 0; b < kNumBuckets; ++b) {
+          if (dbg[b * 4 + 2] == 0) continue;
+          fprintf(f, "%d edges %llu pending %llu rounds %llu us %.1f\n", b, dbg[b * 4 + 2], dbg[b * 4 + 3],
+                  dbg[b * 4 + 1] - prev, dbg[b * 4 + 0] / 1000.0);
+          prev = dbg[b * 4 + 1];
+        }
+        fclose(f);
+      }
     }
     if (stats4) {
       float ms;

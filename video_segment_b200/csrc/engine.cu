@@ -1,0 +1,887 @@
+// engine.cu -- streaming dense over-segmentation engine behind the C ABI (include/vsb200.h).
+// Host-side mirror of DenseSegmentation (segmentation/dense_segmentation.cpp:50-162,268-432) and of
+// the result half of Segmentation (segmentation/segmentation.cpp:392-582,671-773): chunk
+// arithmetic, constraint hand-over between chunks, region ids, per-frame SegmentationDesc
+// arrays.  Every per-pixel / per-edge step is a CUDA kernel launch (preprocess.cu, edges.cu,
+// sort.cu, merge.cu, results.cu); the host only keeps O(#regions + #scan intervals) bookkeeping.
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vsb200.h"
+#include "common.cuh"
+#include "host_shape.hpp"
+#include "results.cuh"
+
+using namespace vsb;
+using vsbh::Region;
+
+namespace {
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct FrameOut {
+  int width, height, chunk_id, chunk_size, overlap_start, hierarchy_frame_idx, connectedness;
+  std::vector<int32_t> region_id, interval_offset, intervals;
+  std::vector<float> moments;
+  std::vector<int32_t> compound, neighbor_offset, neighbor_id;
+  std::vector<int32_t> id_map;   // optional
+  int64_t pts;
+};
+
+#define ENG_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VSB200_ERR_CUDA;                                                               \
+    }                                                                                       \
+  } while (0)
+#define ENG_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+}  // namespace
+
+struct vsb200_dense {
+  vsb200_dense_opts o;
+  int w = 0, h = 0, n = 0;
+  bool use_flow = false, l1 = false;
+  cudaStream_t stream = nullptr;
+  // DenseSegmentation members (dense_segmentation.h:198-230)
+  int input_frames = 0, chunk_id = 0, overlap_frames = 2, constraint_frames = 1;
+  int max_region_id = 0, num_output_frames = 0, curr_chunk_start = 0;
+  int buffered = 0;              // == feature_buffer_.size(): graph slots in use
+  int max_slots = 0;
+  int min_region_size = 0;
+  // device memory
+  uint8_t* d_bgr = nullptr; uint8_t* h_bgr = nullptr;     // staging (pinned host + device)
+  float* h_flow_stage = nullptr;
+  void* d_pre_scratch = nullptr;
+  std::vector<float*> d_frames, d_spatial, d_temporal;     // per slot
+  float* d_flows = nullptr;                                  // [max_slots][n][2]
+  std::vector<std::vector<float>> h_flows;                   // host copies per slot (tube matching)
+  uint32_t* d_codes = nullptr; unsigned long long* d_bstart = nullptr; void* d_sort_scratch = nullptr;
+  size_t sort_scratch_bytes_ = 0;
+  int* d_parent = nullptr; RegionRec* d_rec = nullptr;
+  MergeParams mp{};
+  unsigned long long live_cap_alloc = 0;
+  int* d_labels = nullptr; int* d_idimg = nullptr; int* d_size_adjust = nullptr;
+  int* d_slice_ids = nullptr; unsigned* d_row_counts = nullptr; unsigned* d_row_offsets = nullptr;
+  unsigned* d_total = nullptr;
+  RunRec* d_runs = nullptr; size_t runs_cap = 0;
+  int* d_tmp_ids = nullptr; int2* d_tmp_info = nullptr; size_t tmp_cap = 0;
+  unsigned long long* d_pair_table = nullptr; unsigned long long* d_pairs = nullptr; unsigned long long* d_pair_count = nullptr;
+  unsigned pair_table_cap = 1u << 22; unsigned long long pairs_cap = 1u << 21;
+  int* d_con_ids[2] = {nullptr, nullptr};   // constraint id maps for slot 0 (virtual) and slot 1
+  int* d_first_of_id = nullptr; size_t first_of_id_cap = 0;
+  // host results
+  std::vector<std::unique_ptr<FrameOut>> overlap_out;   // overlap_segmentations_
+  std::deque<std::unique_ptr<FrameOut>> ready;
+  std::deque<int64_t> pts_queue;
+  std::unique_ptr<FrameOut> last_popped;
+  std::vector<uint8_t> proto_buf;
+  bool have_import = false;
+  double stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+  ~vsb200_dense() { release(); }
+  void release();
+  int init();
+  int push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready);
+  int flush(int* n_ready);
+  int add_frame_to_graph(int slot, const int* d_constraints);
+  int start_constrained_chunk();
+  int chunk_boundary(bool flush_all, int* n_ready);
+  int segment_and_output(bool flush_all, std::vector<std::unique_ptr<FrameOut>>* results);
+  int merge_constrained_regions(int slots);
+  int upload_id_map(const FrameOut& f, int* dst);
+};
+
+void vsb200_dense::release() {
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(d_bgr); F(d_pre_scratch); F(d_flows); F(d_codes); F(d_bstart); F(d_sort_scratch); F(d_parent); F(d_rec);
+  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.counters);
+  F(d_labels); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
+  F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
+  F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
+  for (auto p : d_frames) F(p);
+  for (auto p : d_spatial) F(p);
+  for (auto p : d_temporal) F(p);
+  if (h_bgr) cudaFreeHost(h_bgr);
+  if (h_flow_stage) cudaFreeHost(h_flow_stage);
+  if (stream) cudaStreamDestroy(stream);
+  d_bgr = nullptr; stream = nullptr;
+}
+
+int vsb200_dense::init() {
+  ENG_CUDA(cudaSetDevice(o.device));
+  ENG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  n = w * h;
+  max_slots = o.chunk_size + 1;                 // later chunks: virtual + constrained + chunk_size - 1
+  const size_t nodes = (size_t)n * max_slots;
+  if ((unsigned long long)(2 * max_slots - 1) * (unsigned long long)n >= (1ull << 28)) {
+    set_error("frame %dx%d x %d slots overflows the 32-bit edge code (SURVEY config D needs 64-bit codes)", w, h, max_slots);
+    return VSB200_ERR_UNSUPPORTED;
+  }
+  // min_region_size: float product truncated (dense_segmentation.cpp:270-272)
+  min_region_size = (int)(o.frac_min_region_size * w * o.frac_min_region_size * h * o.chunk_size);
+  ENG_CUDA(cudaMalloc(&d_bgr, (size_t)n * 3));
+  ENG_CUDA(cudaMallocHost(&h_bgr, (size_t)n * 3));
+  ENG_CUDA(cudaMalloc(&d_pre_scratch, preprocess_scratch_bytes()));
+  d_frames.assign(max_slots, nullptr); d_spatial.assign(max_slots, nullptr); d_temporal.assign(max_slots, nullptr);
+  for (int s = 0; s < max_slots; ++s) {
+    ENG_CUDA(cudaMalloc(&d_frames[s], (size_t)n * 3 * sizeof(float)));
+    ENG_CUDA(cudaMalloc(&d_spatial[s], (size_t)n * 4 * sizeof(float)));
+    ENG_CUDA(cudaMalloc(&d_temporal[s], (size_t)n * 9 * sizeof(float)));
+  }
+  if (use_flow) {
+    ENG_CUDA(cudaMalloc(&d_flows, nodes * 2 * sizeof(float)));
+    ENG_CUDA(cudaMemsetAsync(d_flows, 0, nodes * 2 * sizeof(float), stream));
+    ENG_CUDA(cudaMallocHost(&h_flow_stage, (size_t)n * 2 * sizeof(float)));
+    h_flows.assign(max_slots, std::vector<float>());
+  }
+  const size_t total_elems = (size_t)n * (4 * max_slots + 9 * (max_slots - 1));
+  ENG_CUDA(cudaMalloc(&d_codes, total_elems * sizeof(uint32_t)));
+  ENG_CUDA(cudaMalloc(&d_bstart, sizeof(unsigned long long) * (kNumBuckets + 1)));
+  sort_scratch_bytes_ = sort_scratch_bytes(2 * max_slots - 1, w, h);
+  ENG_CUDA(cudaMalloc(&d_sort_scratch, sort_scratch_bytes_));
+  ENG_CUDA(cudaMalloc(&d_parent, nodes * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_rec, nodes * sizeof(RegionRec)));
+  ENG_CUDA(cudaMalloc(&mp.res, nodes * 8));
+  ENG_CUDA(cudaMalloc(&mp.acc, nodes * 32));
+  ENG_CUDA(cudaMalloc(&mp.cl, nodes * 4));
+  ENG_CUDA(cudaMalloc(&mp.hull, nodes * 32));
+  ENG_CUDA(cudaMalloc(&mp.counters, 16 * 8));
+  mp.stats = mp.counters + 8;
+  mp.debug = nullptr;
+  ENG_CUDA(cudaMemsetAsync(mp.res, 0xff, nodes * 8, stream));
+  ENG_CUDA(cudaMemsetAsync(mp.acc, 0, nodes * 32, stream));
+  ENG_CUDA(cudaMemsetAsync(mp.counters, 0, 16 * 8, stream));
+  ENG_RC(launch_init_iota(mp.cl, (long long)nodes, stream));
+  ENG_RC(launch_init_hull(mp.hull, (long long)nodes, stream));
+  ENG_CUDA(cudaMalloc(&d_labels, nodes * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_idimg, nodes * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_size_adjust, (nodes + 1) * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_slice_ids, max_slots * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_row_counts, (size_t)max_slots * h * sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_row_offsets, (size_t)max_slots * h * sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_total, sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_pair_table, sizeof(unsigned long long) * pair_table_cap));
+  ENG_CUDA(cudaMalloc(&d_pairs, sizeof(unsigned long long) * pairs_cap));
+  ENG_CUDA(cudaMalloc(&d_pair_count, sizeof(unsigned long long)));
+  ENG_CUDA(cudaMalloc(&d_con_ids[0], (size_t)n * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_con_ids[1], (size_t)n * sizeof(int)));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// AddGenericImage[Constrained] + ConnectTemporally (segmentation.h:310-338): nodes of the slot and
+// the weights of bucket lists 2*slot (spatial) and 2*slot-1 (temporal to slot-1).
+int vsb200_dense::add_frame_to_graph(int slot, const int* d_constraints) {
+  ENG_RC(launch_init_nodes(d_frames[slot], d_constraints, slot, w, h, d_parent, d_rec, stream));
+  const bool temporal = slot >= 1 && !(chunk_id > 0 && slot == 1);   // slot 1 of later chunks: virtual edges only
+  const float* flow = (use_flow && temporal) ? d_flows + (size_t)slot * n * 2 : nullptr;
+  ENG_RC(launch_edge_build(d_frames[slot], temporal ? d_frames[slot - 1] : nullptr, flow, w, h, l1, d_spatial[slot],
+                           temporal ? d_temporal[slot] : nullptr, stream));
+  stats[7] += 2;
+  return 0;
+}
+
+int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready) {
+  if (n_ready) *n_ready = 0;
+  if (!bgr || stride < w * 3) { set_error("push: bad frame buffer"); return VSB200_ERR_INVALID; }
+  if (use_flow && input_frames > 0 && !flow) { set_error("push: flow missing (created with use_flow)"); return VSB200_ERR_INVALID; }
+  if (buffered >= max_slots) { set_error("push: internal slot overflow"); return VSB200_ERR_INVALID; }
+  ENG_CUDA(cudaSetDevice(o.device));
+  pts_queue.push_back(pts);
+  const double t0 = now_ms();
+  const int slot = buffered;
+  // H2D: pinned staging (the caller may release its buffer when push returns)
+  for (int y = 0; y < h; ++y) memcpy(h_bgr + (size_t)y * w * 3, bgr + (size_t)y * stride, (size_t)w * 3);
+  ENG_CUDA(cudaMemcpyAsync(d_bgr, h_bgr, (size_t)n * 3, cudaMemcpyHostToDevice, stream));
+  ENG_RC(launch_preprocess(d_bgr, w * 3, w, h, o.presmoothing, d_frames[slot], d_pre_scratch, stream));
+  stats[7] += (o.presmoothing == 2) ? 3 : 1;
+  if (use_flow) {
+    if (input_frames == 0 || !flow) {
+      h_flows[slot].clear();
+      ENG_CUDA(cudaMemsetAsync(d_flows + (size_t)slot * n * 2, 0, (size_t)n * 2 * sizeof(float), stream));
+    } else {
+      h_flows[slot].resize((size_t)n * 2);
+      for (int y = 0; y < h; ++y)
+        memcpy(h_flows[slot].data() + (size_t)y * w * 2, (const char*)flow + (size_t)y * flow_stride, sizeof(float) * 2 * w);
+      ENG_CUDA(cudaStreamSynchronize(stream));       // staging buffer reuse
+      memcpy(h_flow_stage, h_flows[slot].data(), sizeof(float) * 2 * n);
+      ENG_CUDA(cudaMemcpyAsync(d_flows + (size_t)slot * n * 2, h_flow_stage, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, stream));
+    }
+  }
+  ENG_RC(add_frame_to_graph(slot, nullptr));
+  ENG_CUDA(cudaStreamSynchronize(stream));            // h_bgr is reused by the next push
+  stats[0] += now_ms() - t0;
+  ++buffered;
+  ++input_frames;
+  if (buffered - curr_chunk_start >= o.chunk_size) return chunk_boundary(false, n_ready);
+  return 0;
+}
+
+int vsb200_dense::flush(int* n_ready) {
+  if (n_ready) *n_ready = 0;
+  if (buffered == 0) return 0;
+  ENG_CUDA(cudaSetDevice(o.device));
+  return chunk_boundary(true, n_ready);
+}
+
+// Renders the region-id image of a result (SegmentationDescToIdImage, segmentation_util.cpp:741-770)
+// and uploads it as the constraint ids of the next chunk.
+int vsb200_dense::upload_id_map(const FrameOut& f, int* dst) {
+  std::vector<int32_t> img((size_t)n, 0);
+  for (size_t k = 0; k < f.region_id.size(); ++k)
+    for (int q = f.interval_offset[k]; q < f.interval_offset[k + 1]; ++q) {
+      const int y = f.intervals[3 * q], lx = f.intervals[3 * q + 1], rx = f.intervals[3 * q + 2];
+      std::fill(img.begin() + (size_t)y * w + lx, img.begin() + (size_t)y * w + rx + 1, f.region_id[k]);
+    }
+  ENG_CUDA(cudaMemcpyAsync(dst, img.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// ChunkBoundaryOutput, second half (dense_segmentation.cpp:290-328): slot 0 = virtual copy of the
+// last output frame, slot 1 = next frame re-added with its previous labels as constraints.
+int vsb200_dense::start_constrained_chunk() {
+  // d_con_ids[0/1] hold the id maps; slot 1 already owns its smoothed frame (pointer swap done by caller)
+  size_t need = (size_t)max_region_id + 2;
+  if (need > first_of_id_cap) {
+    if (d_first_of_id) cudaFree(d_first_of_id);
+    first_of_id_cap = need * 2;
+    ENG_CUDA(cudaMalloc(&d_first_of_id, first_of_id_cap * sizeof(int)));
+  }
+  ENG_RC(launch_init_virtual_nodes(d_con_ids[0], 0, w, h, d_parent, d_rec, d_first_of_id, max_region_id + 1, stream));
+  ENG_RC(add_frame_to_graph(1, d_con_ids[1]));
+  stats[7] += 3;
+  return 0;
+}
+
+int vsb200_dense::chunk_boundary(bool flush_all, int* n_ready) {
+  std::vector<std::unique_ptr<FrameOut>> results;
+  ENG_RC(segment_and_output(flush_all, &results));
+  for (auto& r : results) {
+    r->pts = pts_queue.front();
+    pts_queue.pop_front();
+    ready.push_back(std::move(r));
+  }
+  if (n_ready) *n_ready = (int)results.size();
+  if (flush_all) return 0;
+  // new Segmentation with curr_chunk_start_ + chunk_size slots (dense_segmentation.cpp:294-298)
+  ENG_RC(upload_id_map(*overlap_out[0], d_con_ids[0]));
+  ENG_RC(upload_id_map(*overlap_out[1], d_con_ids[1]));
+  ENG_RC(start_constrained_chunk());
+  overlap_out.clear();
+  return 0;
+}
+
+// MergeConstrainedRegions (segmentation_graph.h:703-786), host assisted: the device lists the
+// distinct representatives met on the constrained slot in first-occurrence order; the O(#regions)
+// decision walk runs on the host and its unions / constraint resets are written back.
+namespace {
+__global__ void mcr_first_kernel(const int* __restrict__ labels_slot1, int base, int n, int* __restrict__ first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(&first[labels_slot1[i]], base + i);
+}
+__global__ void mcr_collect_kernel(const int* __restrict__ labels_slot1, int base, int n, int* __restrict__ first,
+                                   int2* __restrict__ out, unsigned* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = labels_slot1[i];
+  if (first[r] == base + i) {
+    const unsigned k = atomicAdd(count, 1u);
+    out[k] = make_int2(base + i, r);
+    first[r] = 0x7f7f7f7f;      // restore scratch
+  }
+}
+__global__ void gather_rec_kernel(const int* __restrict__ ids, int m, const RegionRec* __restrict__ rec, RegionRec* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = rec[ids[i]];
+}
+__global__ void scatter_rec_kernel(const int* __restrict__ ids, const int* __restrict__ parents, int m,
+                                   const RegionRec* __restrict__ recs, RegionRec* __restrict__ rec, int* __restrict__ parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  rec[ids[i]] = recs[i];
+  parent[ids[i]] = parents[i];
+}
+}  // namespace
+
+int vsb200_dense::merge_constrained_regions(int slots) {
+  // roots of slot 1 nodes
+  ENG_RC(launch_flatten(d_parent, nullptr, d_labels, (long long)n * 2, stream));     // slots 0 and 1
+  int* first = mp.cl;   // scratch (identity outside a merge launch) -> use hull flags instead? use d_size_adjust
+  first = d_size_adjust;
+  ENG_CUDA(cudaMemsetAsync(first, 0x7f, ((size_t)n * slots + 1) * sizeof(int), stream));
+  int2* d_list = (int2*)d_runs;   // runs buffer is free at this point
+  if (runs_cap < (size_t)n) {
+    if (d_runs) cudaFree(d_runs);
+    runs_cap = (size_t)n * 2;
+    ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
+    d_list = (int2*)d_runs;
+  }
+  ENG_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned), stream));
+  mcr_first_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_labels + n, n, n, first);
+  mcr_collect_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_labels + n, n, n, first, d_list, d_total);
+  unsigned cnt = 0;
+  ENG_CUDA(cudaMemcpyAsync(&cnt, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  std::vector<int2> list(cnt);
+  if (cnt) ENG_CUDA(cudaMemcpy(list.data(), d_list, sizeof(int2) * cnt, cudaMemcpyDeviceToHost));
+  std::sort(list.begin(), list.end(), [](const int2& a, const int2& b) { return a.x < b.x; });
+  // virtual representatives: first pixel of every constraint id on slot 0 (from the overlap result)
+  std::vector<int> ids;          // device node ids whose records take part
+  std::unordered_map<int, int> pos;   // node id -> local index
+  auto local = [&](int id) { auto it = pos.find(id); if (it != pos.end()) return it->second; pos[id] = (int)ids.size(); ids.push_back(id); return (int)ids.size() - 1; };
+  for (const auto& e : list) local(e.y);
+  std::vector<std::pair<int, int>> virt;   // (constraint id, local index of virtual rep)
+  {
+    std::vector<int> h_first((size_t)max_region_id + 1);
+    ENG_CUDA(cudaMemcpy(h_first.data(), d_first_of_id, sizeof(int) * ((size_t)max_region_id + 1), cudaMemcpyDeviceToHost));
+    for (int c = 0; c <= max_region_id; ++c)
+      if (h_first[c] != 0x7f7f7f7f) virt.emplace_back(c, local(h_first[c]));
+  }
+  const int m = (int)ids.size();
+  if (m == 0) return 0;
+  if (tmp_cap < (size_t)m) {
+    if (d_tmp_ids) cudaFree(d_tmp_ids);
+    if (d_tmp_info) cudaFree(d_tmp_info);
+    tmp_cap = (size_t)m * 2 + 1024;
+    ENG_CUDA(cudaMalloc(&d_tmp_ids, tmp_cap * 2 * sizeof(int)));
+    ENG_CUDA(cudaMalloc(&d_tmp_info, tmp_cap * sizeof(RegionRec)));
+  }
+  RegionRec* d_recs = (RegionRec*)d_tmp_info;
+  ENG_CUDA(cudaMemcpyAsync(d_tmp_ids, ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+  gather_rec_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_tmp_ids, m, d_rec, d_recs);
+  std::vector<RegionRec> recs(m);
+  ENG_CUDA(cudaMemcpyAsync(recs.data(), d_recs, sizeof(RegionRec) * m, cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  std::vector<int> par(m);
+  for (int i = 0; i < m; ++i) par[i] = i;
+  auto find = [&](int x) { while (par[x] != x) { par[x] = par[par[x]]; x = par[x]; } return x; };
+  auto dist = [&](const RegionRec& a, const RegionRec& b) {
+    const float d1 = a.d0 - b.d0, d2 = a.d1 - b.d1, d3 = a.d2 - b.d2;
+    return std::sqrt((d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / 3.0f));   // edge weight 1.0: no force merge
+  };
+  auto merge = [&](int a, int b) {                 // MergeRegions(rep_1 = a, rep_2 = b)
+    const bool aw = recs[a].sz > recs[b].sz;
+    const int mi = aw ? a : b, oi = aw ? b : a;
+    RegionRec& M = recs[mi];
+    const RegionRec& O = recs[oi];
+    const float denom = 1.0f / (float)(O.sz + M.sz);
+    const float fa = (float)O.sz * denom, fb = (float)M.sz * denom;
+    M.d0 = fa * O.d0 + fb * M.d0; M.d1 = fa * O.d1 + fb * M.d1; M.d2 = fa * O.d2 + fb * M.d2;
+    M.sz += O.sz;
+    M.con = std::max(recs[a].con, recs[b].con);
+    par[oi] = mi;
+  };
+  std::unordered_map<int, int> con2rep;
+  auto visit = [&](int my) {
+    // one step of the non-virtual loop (:722-760) for representative `my`
+    auto it = con2rep.find(recs[my].con);
+    if (it == con2rep.end()) { con2rep[recs[my].con] = my; return; }
+    const int cr = find(it->second);
+    if (cr == my) return;
+    const float d = dist(recs[my], recs[cr]);
+    if (d > 0.15f) {
+      if ((double)recs[my].sz < (double)recs[cr].sz * 0.3) recs[my].con = -1;
+      else if ((double)recs[cr].sz < (double)recs[my].sz * 0.3) { recs[cr].con = -1; it->second = my; }
+      else { recs[my].con = -1; recs[cr].con = -1; con2rep.erase(it); }
+    } else {
+      merge(my, cr);
+    }
+  };
+  for (const auto& e : list) {
+    int my = find(pos[e.y]);
+    const int before = recs[my].con;
+    visit(my);
+    my = find(my);
+    // a representative that lost its constraint is looked up again under key -1 by its next node
+    if (before >= 0 && recs[my].con < 0) visit(my);
+  }
+  for (const auto& v : virt) {                        // virtual nodes: always merge (:763-785)
+    const int my = find(v.second);
+    auto it = con2rep.find(recs[my].con);
+    if (it == con2rep.end()) { con2rep[recs[my].con] = my; continue; }
+    const int cr = find(it->second);
+    if (cr != my) merge(my, cr);
+  }
+  std::vector<int> parents(m);
+  for (int i = 0; i < m; ++i) parents[i] = ids[find(i)];
+  ENG_CUDA(cudaMemcpyAsync(d_tmp_ids + tmp_cap, parents.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+  ENG_CUDA(cudaMemcpyAsync(d_recs, recs.data(), sizeof(RegionRec) * m, cudaMemcpyHostToDevice, stream));
+  scatter_rec_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_tmp_ids, d_tmp_ids + tmp_cap, m, d_recs, d_rec, d_parent);
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  stats[7] += 5;
+  return 0;
+}
+
+// SegmentAndOutputChunk (dense_segmentation.cpp:330-432) with RunOverSegmentation
+// (segmentation.cpp:272-303) inlined.
+int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr<FrameOut>>* results) {
+  const int slots = buffered;
+  const bool constrained_chunk = chunk_id > 0;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) cudaEventCreate(&e);
+  // ---------------- sort ----------------
+  const int num_lists = 2 * slots - 1;
+  std::vector<const float*> seg(num_lists, nullptr);
+  for (int s = 0; s < slots; ++s) {
+    if (!(constrained_chunk && s == 0)) seg[2 * s] = d_spatial[s];              // virtual slot: no spatial edges
+    if (s >= 1 && !(constrained_chunk && s == 1)) seg[2 * s - 1] = d_temporal[s];   // virtual edges carry no weight
+  }
+  cudaEventRecord(ev[0], stream);
+  ENG_RC(launch_sort_edges(seg.data(), num_lists, w, h, d_codes, d_bstart, d_sort_scratch, sort_scratch_bytes_, stream));
+  stats[7] += 5;
+  unsigned long long h_bstart[kNumBuckets + 1];
+  ENG_CUDA(cudaMemcpyAsync(h_bstart, d_bstart, sizeof(h_bstart), cudaMemcpyDeviceToHost, stream));
+  cudaEventRecord(ev[1], stream);
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  unsigned long long max_bucket = 1;
+  for (int b = 0; b < kNumBuckets; ++b) max_bucket = std::max(max_bucket, h_bstart[b + 1] - h_bstart[b]);
+  if (max_bucket > live_cap_alloc) {
+    if (mp.live_a) cudaFree(mp.live_a);
+    if (mp.live_b) cudaFree(mp.live_b);
+    live_cap_alloc = max_bucket + max_bucket / 4;
+    ENG_CUDA(cudaMalloc(&mp.live_a, live_cap_alloc * 16));
+    ENG_CUDA(cudaMalloc(&mp.live_b, live_cap_alloc * 16));
+  }
+  // ---------------- merge ----------------
+  mp.w = w; mp.h = h; mp.slots = slots; mp.min_region_size = min_region_size;
+  mp.force_merge_weight = l1 ? 0.002f : 0.001f;
+  mp.has_constraints = constrained_chunk ? 1 : 0;
+  mp.flows = use_flow ? d_flows : nullptr;
+  mp.codes = d_codes; mp.bucket_start = d_bstart; mp.parent = d_parent; mp.rec = d_rec;
+  mp.live_cap = live_cap_alloc;
+  ENG_CUDA(cudaMemsetAsync(mp.stats, 0, 8 * 8, stream));
+  ENG_RC(launch_merge(mp, stream));
+  stats[7] += 1;
+  if (constrained_chunk) ENG_RC(merge_constrained_regions(slots));
+  cudaEventRecord(ev[2], stream);
+  // ---------------- labels, N4, RLE ----------------
+  const size_t nodes = (size_t)n * slots;
+  ENG_RC(launch_flatten(d_parent, nullptr, d_labels, (long long)nodes, stream));
+  ENG_CUDA(cudaMemcpyAsync(d_idimg, d_labels, nodes * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  ENG_CUDA(cudaMemsetAsync(d_size_adjust, 0, (nodes + 1) * sizeof(int), stream));
+  std::vector<int> slice_ids;
+  for (int s = 0; s < slots; ++s) if (!(constrained_chunk && s == 0)) slice_ids.push_back(s);
+  const int ns = (int)slice_ids.size();
+  ENG_CUDA(cudaMemcpyAsync(d_slice_ids, slice_ids.data(), ns * sizeof(int), cudaMemcpyHostToDevice, stream));
+  if (o.enforce_n4_connectivity) ENG_RC(launch_n4(d_idimg, w, h, ns, d_slice_ids, d_size_adjust, stream));
+  ENG_RC(launch_rle_count(d_idimg, w, h, d_slice_ids, ns, d_row_counts, stream));
+  ENG_RC(launch_scan_u32(d_row_counts, d_row_offsets, d_total, ns * h, stream));
+  unsigned n_runs = 0;
+  ENG_CUDA(cudaMemcpyAsync(&n_runs, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  if (n_runs > runs_cap) {
+    if (d_runs) cudaFree(d_runs);
+    runs_cap = (size_t)n_runs + n_runs / 2 + 1024;
+    ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
+  }
+  ENG_RC(launch_rle_write(d_idimg, w, h, d_slice_ids, ns, d_row_offsets, d_runs, stream));
+  std::vector<RunRec> runs(n_runs);
+  ENG_CUDA(cudaMemcpyAsync(runs.data(), d_runs, sizeof(RunRec) * n_runs, cudaMemcpyDeviceToHost, stream));
+  unsigned long long h_stats[8];
+  ENG_CUDA(cudaMemcpyAsync(h_stats, mp.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+  cudaEventRecord(ev[3], stream);
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  stats[7] += 6;
+  stats[8] += (double)h_stats[0];
+  const double t_host0 = now_ms();
+  // ---------------- regions in first-seen order (ObtainResults, :533-559) ----------------
+  std::vector<std::unique_ptr<Region>> regions;
+  std::unordered_map<int, int> label2region;
+  label2region.reserve(1 << 14);
+  for (const RunRec& r : runs) {
+    auto it = label2region.find(r.id);
+    int ri;
+    if (it == label2region.end()) {
+      ri = (int)regions.size();
+      label2region[r.id] = ri;
+      regions.emplace_back(new Region);
+      regions.back()->index = ri;
+      regions.back()->label = r.id;
+    } else {
+      ri = it->second;
+    }
+    Region& R = *regions[ri];
+    if (R.raster.empty() || R.raster.back().frame < r.slice)
+      R.raster.push_back(vsbh::Slice{r.slice, std::make_shared<vsbh::Raster>()});
+    R.raster.back().raster->push_back(vsbh::Interval{r.y, r.left_x, r.right_x});
+  }
+  // sizes / constraints of the representatives (GetCreateRegionInformation + size_adjust_map)
+  {
+    const int m = (int)regions.size();
+    if (tmp_cap < (size_t)m) {
+      if (d_tmp_ids) cudaFree(d_tmp_ids);
+      if (d_tmp_info) cudaFree(d_tmp_info);
+      tmp_cap = (size_t)m * 2 + 1024;
+      ENG_CUDA(cudaMalloc(&d_tmp_ids, tmp_cap * 2 * sizeof(int)));
+      ENG_CUDA(cudaMalloc(&d_tmp_info, tmp_cap * sizeof(RegionRec)));
+    }
+    std::vector<int> ids(m);
+    for (int i = 0; i < m; ++i) ids[i] = regions[i]->label;
+    std::vector<int2> info(m);
+    ENG_CUDA(cudaMemcpyAsync(d_tmp_ids, ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
+    ENG_RC(launch_gather_region_info(d_tmp_ids, m, d_rec, d_size_adjust, (int2*)d_tmp_info, stream));
+    ENG_CUDA(cudaMemcpyAsync(info.data(), d_tmp_info, sizeof(int2) * m, cudaMemcpyDeviceToHost, stream));
+    ENG_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < m; ++i) { regions[i]->size = info[i].x; regions[i]->constrained_id = info[i].y; }
+    stats[7] += 1;
+  }
+  // ---------------- EnforceSpatialConnectedness (:666-904) ----------------
+  std::vector<RunRec> relabel;
+  if (o.enforce_spatial_connectedness) {
+    std::vector<const float*> flows;
+    if (use_flow) for (int s = 0; s < slots; ++s) flows.push_back(h_flows[s].empty() ? nullptr : h_flows[s].data());
+    int next_label = (int)nodes;
+    const int num_regions = (int)regions.size();
+    for (int r = 0; r < num_regions; ++r) {
+      std::vector<vsbh::Tube> tubes = vsbh::split_region_into_tubes(regions[r]->raster, w, h, use_flow ? &flows : nullptr);
+      if (tubes.empty()) continue;
+      int keep = -1, keep_score = 0;
+      std::vector<float> areas(tubes.size());
+      for (int k = 0; k < (int)tubes.size(); ++k) {
+        float area = 0;
+        for (const auto& s : tubes[k]) area += s.shape.size;
+        areas[k] = area;
+        if (area > keep_score) { keep_score = area; keep = k; }
+      }
+      for (int k = 0; k < (int)tubes.size(); ++k) {
+        Region* target = regions[r].get();
+        if (k != keep) {
+          regions[r]->size -= areas[k];                 // size_adjust_map[rep] -= area
+          regions.emplace_back(new Region);
+          target = regions.back().get();
+          target->index = (int)regions.size() - 1;
+          target->label = next_label++;
+          target->size = areas[k];
+          target->constrained_id = -1;
+          label2region[target->label] = target->index;
+          for (const auto& s : tubes[k])
+            for (const auto& iv : s.raster) relabel.push_back(RunRec{s.frame, iv.y, iv.lx, iv.rx, target->label});
+        }
+        target->raster.clear();
+        for (auto& s : tubes[k]) {
+          auto nr = std::make_shared<vsbh::Raster>();
+          nr->swap(s.raster);
+          target->raster.push_back(vsbh::Slice{s.frame, nr});
+        }
+      }
+    }
+  }
+  stats[5] += now_ms() - t_host0;
+  // ---------------- neighbours (DetermineNeighborIdsImpl, segmentation_graph.h:466-496) ----------------
+  if (!relabel.empty()) {
+    if (relabel.size() > runs_cap) {
+      if (d_runs) cudaFree(d_runs);
+      runs_cap = relabel.size() * 2;
+      ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
+    }
+    ENG_CUDA(cudaMemcpyAsync(d_runs, relabel.data(), sizeof(RunRec) * relabel.size(), cudaMemcpyHostToDevice, stream));
+    ENG_RC(launch_relabel(d_runs, (int)relabel.size(), w, h, d_labels, stream));
+  }
+  ENG_RC(launch_neighbor_pairs(d_labels, w, h, slots, use_flow ? d_flows : nullptr, constrained_chunk ? 1 : 0,
+                               d_pair_table, pair_table_cap, d_pairs, d_pair_count, pairs_cap, stream));
+  unsigned long long n_pairs = 0;
+  ENG_CUDA(cudaMemcpyAsync(&n_pairs, d_pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));
+  cudaEventRecord(ev[4], stream);
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  if (n_pairs > pairs_cap || n_pairs * 2 > pair_table_cap) {
+    set_error("neighbour pair table overflow (%llu pairs)", n_pairs);
+    return VSB200_ERR_CUDA;
+  }
+  std::vector<unsigned long long> pairs(n_pairs);
+  if (n_pairs) ENG_CUDA(cudaMemcpy(pairs.data(), d_pairs, sizeof(unsigned long long) * n_pairs, cudaMemcpyDeviceToHost));
+  stats[7] += 3;
+  const double t_host1 = now_ms();
+  for (unsigned long long key : pairs) {
+    const int la = (int)(key >> 32), lb = (int)(key & 0xffffffffu);
+    auto ia = label2region.find(la), ib = label2region.find(lb);
+    if (ia == label2region.end() || ib == label2region.end()) continue;   // virtual-only representatives: never output
+    regions[ia->second]->neighbors.push_back(ib->second);
+    regions[ib->second]->neighbors.push_back(ia->second);
+  }
+  for (auto& R : regions) {
+    std::sort(R->neighbors.begin(), R->neighbors.end());
+    R->neighbors.erase(std::unique(R->neighbors.begin(), R->neighbors.end()), R->neighbors.end());
+  }
+  // ---------------- result shaping (dense_segmentation.cpp:335-398) ----------------
+  const int overlap_start = slots - (flush_all ? 0 : overlap_frames);
+  const int last_output_frame = std::min(slots - 1, overlap_start);
+  const int max_result_frame = std::min(slots - 1, last_output_frame + constraint_frames);
+  // ConstrainSegmentationToFrameInterval(0, last_output_frame + 1) (segmentation.cpp:392-403)
+  for (auto& R : regions)
+    if (R->raster.empty() || R->raster.front().frame >= last_output_frame + 1 || R->raster.back().frame < 0) R->removed = true;
+  // AdjustRegionAreaToFrameInterval (segmentation.cpp:424-441)
+  for (auto& R : regions)
+    for (const auto& sl : R->raster)
+      if (sl.frame < 0 || sl.frame >= last_output_frame + 1) R->size -= vsbh::raster_area(*sl.raster);
+  // AssignUniqueRegionIds (segmentation.cpp:549-582)
+  const bool use_constraints = constrained_chunk;
+  int max_id = -1;
+  for (auto& R : regions) {
+    R->region_id = (use_constraints && R->constrained_id >= 0) ? R->constrained_id : R->index + max_region_id;
+    max_id = std::max(max_id, R->region_id);
+  }
+  max_region_id = std::max(max_region_id, max_id + 1);
+  const int chunk_sz = last_output_frame - curr_chunk_start + 1;
+  const int hierarchy_frame_idx = num_output_frames;
+  std::vector<int32_t> idmap_host;
+  for (int f = curr_chunk_start; f <= max_result_frame; ++f) {
+    // RetrieveSegmentation3D (segmentation.cpp:458-533)
+    std::unique_ptr<FrameOut> out(new FrameOut);
+    out->width = w; out->height = h; out->chunk_id = chunk_id;
+    out->connectedness = o.enforce_n4_connectivity ? 1 : 2;
+    out->chunk_size = chunk_sz; out->overlap_start = chunk_sz; out->hierarchy_frame_idx = hierarchy_frame_idx;
+    out->pts = 0;
+    struct Item { int id; const vsbh::Raster* raster; };
+    std::vector<Item> items;
+    for (const auto& R : regions) {
+      auto it = std::lower_bound(R->raster.begin(), R->raster.end(), f,
+                                 [](const vsbh::Slice& a, int fr) { return a.frame < fr; });
+      if (it == R->raster.end() || it->frame != f) continue;
+      items.push_back(Item{R->region_id, it->raster.get()});
+    }
+    if (use_constraints) std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.id < b.id; });
+    out->interval_offset.push_back(0);
+    for (const Item& it : items) {
+      out->region_id.push_back(it.id);
+      for (const auto& iv : *it.raster) {
+        out->intervals.push_back(iv.y); out->intervals.push_back(iv.lx); out->intervals.push_back(iv.rx);
+      }
+      out->interval_offset.push_back((int32_t)(out->intervals.size() / 3));
+      const vsbh::Moments mo = vsbh::moments_of(*it.raster);
+      const float mm[6] = {mo.size, mo.mx, mo.my, mo.xx, mo.xy, mo.yy};
+      out->moments.insert(out->moments.end(), mm, mm + 6);
+    }
+    out->neighbor_offset.push_back(0);
+    if (f == curr_chunk_start) {                         // hierarchy level 0 (segmentation.cpp:702-773)
+      struct Comp { int id, size, sf, ef; std::vector<int> nb; };
+      std::vector<Comp> comps;
+      for (const auto& R : regions) {
+        if (R->removed) continue;
+        Comp c;
+        c.id = R->region_id; c.size = R->size;
+        c.sf = R->raster.front().frame; c.ef = R->raster.back().frame;
+        for (int nb : R->neighbors) if (!regions[nb]->removed) c.nb.push_back(regions[nb]->region_id);
+        if (use_constraints) std::sort(c.nb.begin(), c.nb.end());
+        comps.push_back(std::move(c));
+      }
+      if (use_constraints) std::sort(comps.begin(), comps.end(), [](const Comp& a, const Comp& b) { return a.id < b.id; });
+      for (const Comp& c : comps) {
+        out->compound.push_back(c.id); out->compound.push_back(c.size);
+        out->compound.push_back(c.sf); out->compound.push_back(c.ef);
+        out->neighbor_id.insert(out->neighbor_id.end(), c.nb.begin(), c.nb.end());
+        out->neighbor_offset.push_back((int32_t)out->neighbor_id.size());
+      }
+    }
+    if (o.want_id_maps) {
+      out->id_map.assign((size_t)n, -1);
+      for (size_t k = 0; k < out->region_id.size(); ++k)
+        for (int q = out->interval_offset[k]; q < out->interval_offset[k + 1]; ++q) {
+          const int y = out->intervals[3 * q], lx = out->intervals[3 * q + 1], rx = out->intervals[3 * q + 2];
+          std::fill(out->id_map.begin() + (size_t)y * w + lx, out->id_map.begin() + (size_t)y * w + rx + 1, out->region_id[k]);
+        }
+    }
+    if (f <= last_output_frame) {
+      if (f < last_output_frame) {
+        results->push_back(std::move(out));
+      } else {
+        results->push_back(std::unique_ptr<FrameOut>(new FrameOut(*out)));
+      }
+      ++num_output_frames;
+    }
+    if (f >= last_output_frame && out) overlap_out.push_back(std::move(out));
+  }
+  // feature_buffer_.erase(begin, begin + last_output_frame): the kept frames become slots 0, 1
+  if (!flush_all) {
+    // slot 1 of the next chunk = frame `last_output_frame + 1`; slot 0 (virtual) needs no pixels
+    std::swap(d_frames[1], d_frames[last_output_frame + 1]);
+    if (use_flow) {
+      ENG_CUDA(cudaMemcpyAsync(d_flows + (size_t)1 * n * 2, d_flows + (size_t)(last_output_frame + 1) * n * 2,
+                               (size_t)n * 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+      std::swap(h_flows[1], h_flows[last_output_frame + 1]);
+      h_flows[0].clear();
+    }
+    buffered = overlap_frames;
+    curr_chunk_start = 1;
+  } else {
+    buffered = 0;
+    curr_chunk_start = 0;
+    overlap_out.clear();
+  }
+  ++chunk_id;
+  stats[5] += now_ms() - t_host1;
+  float ms;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]); stats[2] += ms;
+  cudaEventElapsedTime(&ms, ev[1], ev[2]); stats[3] += ms;
+  cudaEventElapsedTime(&ms, ev[2], ev[3]); stats[4] += ms;
+  cudaEventElapsedTime(&ms, ev[3], ev[4]); stats[6] += ms;
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// proto2 wire encoding of segmentation.SegmentationDesc (segment_util/segmentation.proto:55-172)
+// ---------------------------------------------------------------------------
+namespace {
+struct PB {
+  std::vector<uint8_t>& b;
+  void varint(uint64_t v) { while (v >= 0x80) { b.push_back((uint8_t)(v | 0x80)); v >>= 7; } b.push_back((uint8_t)v); }
+  void tag(int field, int wire) { varint((uint64_t)(field << 3 | wire)); }
+  void i32(int field, int32_t v) { tag(field, 0); varint((uint64_t)(int64_t)v); }      // int32: sign-extended varint
+  void f32(int field, float v) { tag(field, 5); uint32_t u; memcpy(&u, &v, 4); for (int i = 0; i < 4; ++i) b.push_back((uint8_t)(u >> (8 * i))); }
+  void bytes(int field, const std::vector<uint8_t>& s) { tag(field, 2); varint(s.size()); b.insert(b.end(), s.begin(), s.end()); }
+};
+
+void encode_proto(const FrameOut& f, std::vector<uint8_t>* out) {
+  out->clear();
+  PB top{*out};
+  std::vector<uint8_t> reg, ras, si, sm;
+  for (size_t k = 0; k < f.region_id.size(); ++k) {        // repeated Region2D region = 2
+    reg.clear(); ras.clear();
+    PB r{reg};
+    r.i32(1, f.region_id[k]);                               // required int32 id = 1
+    PB rs{ras};
+    for (int q = f.interval_offset[k]; q < f.interval_offset[k + 1]; ++q) {
+      si.clear();
+      PB s{si};
+      s.i32(1, f.intervals[3 * q]); s.i32(2, f.intervals[3 * q + 1]); s.i32(3, f.intervals[3 * q + 2]);
+      rs.bytes(1, si);                                      // repeated ScanInterval scan_inter = 1
+    }
+    r.bytes(3, ras);                                        // optional Rasterization raster = 3
+    sm.clear();
+    PB m{sm};
+    for (int j = 0; j < 6; ++j) m.f32(j + 1, f.moments[6 * k + j]);
+    r.bytes(5, sm);                                         // optional ShapeMoments shape_moments = 5
+    top.bytes(2, reg);
+  }
+  if (!f.compound.empty()) {                                // repeated HierarchyLevel hierarchy = 3
+    std::vector<uint8_t> hier, comp;
+    PB hl{hier};
+    const size_t nc = f.compound.size() / 4;
+    for (size_t c = 0; c < nc; ++c) {
+      comp.clear();
+      PB cr{comp};
+      cr.i32(1, f.compound[4 * c]); cr.i32(2, f.compound[4 * c + 1]);
+      for (int q = f.neighbor_offset[c]; q < f.neighbor_offset[c + 1]; ++q) cr.i32(3, f.neighbor_id[q]);
+      cr.i32(6, f.compound[4 * c + 2]); cr.i32(7, f.compound[4 * c + 3]);
+      hl.bytes(2, comp);                                    // repeated CompoundRegion region = 2
+    }
+    top.bytes(3, hier);
+  }
+  top.i32(4, f.width); top.i32(5, f.height); top.i32(6, f.chunk_size); top.i32(7, f.overlap_start);
+  top.i32(8, f.chunk_id); top.i32(9, f.hierarchy_frame_idx); top.i32(12, f.connectedness);
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void vsb200_dense_default_opts(vsb200_dense_opts* o) {
+  if (!o) return;
+  o->presmoothing = 2; o->frac_min_region_size = 0.01f; o->chunk_size = 20; o->chunk_overlap_ratio = 0.2f;
+  o->num_constraint_frames = 1; o->two_stage_oversegment = 0; o->thin_structure_suppression = 0;
+  o->enforce_n4_connectivity = 1; o->enforce_spatial_connectedness = 1; o->color_distance = 1;
+  o->compute_vectorization = 0; o->device = 0; o->want_id_maps = 0;
+}
+
+int vsb200_dense_create(const vsb200_dense_opts* o, int width, int height, int use_flow, vsb200_dense** out) {
+  if (!o || !out || width < 2 || height < 2) { set_error("create: bad arguments"); return VSB200_ERR_INVALID; }
+  if (o->chunk_size < 3) { set_error("Chunk size needs to be at least 3 frames."); return VSB200_ERR_INVALID; }   // dense_segmentation.cpp:54
+  int overlap = (int)(o->chunk_overlap_ratio * o->chunk_size + 0.5f);
+  overlap = std::min(overlap, 2);                                             // dense_segmentation.cpp:59-62
+  if (overlap >= o->chunk_size || overlap < 2) { set_error("Overlap needs to be 2 frames and smaller than chunk_size."); return VSB200_ERR_INVALID; }
+  if (o->num_constraint_frames < 1) { set_error("num_constraint_frames must be >= 1"); return VSB200_ERR_INVALID; }
+  if (o->presmoothing == 1) { set_error("PRESMOOTH_GAUSSIAN (cv::GaussianBlur) is not built"); return VSB200_ERR_UNSUPPORTED; }
+  if (o->two_stage_oversegment || o->thin_structure_suppression || o->compute_vectorization) {
+    set_error("two_stage_oversegment / thin_structure_suppression / compute_vectorization are not built");
+    return VSB200_ERR_UNSUPPORTED;
+  }
+  if (vsb200_device_count() <= 0) { set_error("no sm_100 CUDA device available: this path has no CPU fallback"); return VSB200_ERR_NO_DEVICE; }
+  std::unique_ptr<vsb200_dense> d(new vsb200_dense);
+  d->o = *o; d->w = width; d->h = height; d->use_flow = use_flow != 0; d->l1 = (o->color_distance == 0);
+  d->overlap_frames = overlap;
+  d->constraint_frames = std::min(o->num_constraint_frames, overlap - 1);
+  if (int rc = d->init()) return rc;
+  *out = d.release();
+  return VSB200_OK;
+}
+
+int vsb200_dense_push(vsb200_dense* d, const uint8_t* bgr, int row_stride_bytes, const float* flow_xy,
+                      int flow_row_stride_bytes, int64_t pts, int* n_ready) {
+  if (!d) return VSB200_ERR_INVALID;
+  return d->push(bgr, row_stride_bytes, flow_xy, flow_row_stride_bytes, pts, n_ready);
+}
+
+int vsb200_dense_flush(vsb200_dense* d, int* n_ready) {
+  if (!d) return VSB200_ERR_INVALID;
+  return d->flush(n_ready);
+}
+
+int vsb200_dense_pop(vsb200_dense* d, vsb200_frame_result* out) {
+  if (!d || !out) return VSB200_ERR_INVALID;
+  if (d->ready.empty()) return VSB200_ERR_EMPTY;
+  d->last_popped = std::move(d->ready.front());
+  d->ready.pop_front();
+  const FrameOut& f = *d->last_popped;
+  out->width = f.width; out->height = f.height; out->chunk_id = f.chunk_id; out->chunk_size = f.chunk_size;
+  out->overlap_start = f.overlap_start; out->hierarchy_frame_idx = f.hierarchy_frame_idx;
+  out->connectedness = f.connectedness;
+  out->n_regions = (int32_t)f.region_id.size();
+  out->region_id = f.region_id.data(); out->interval_offset = f.interval_offset.data();
+  out->intervals = f.intervals.data(); out->shape_moments = f.moments.data();
+  out->n_compound = (int32_t)(f.compound.size() / 4);
+  out->compound = f.compound.data(); out->neighbor_offset = f.neighbor_offset.data();
+  out->neighbor_id = f.neighbor_id.data();
+  out->pts = f.pts;
+  return VSB200_OK;
+}
+
+const int32_t* vsb200_dense_last_id_map(vsb200_dense* d) {
+  if (!d || !d->last_popped || d->last_popped->id_map.empty()) return nullptr;
+  return d->last_popped->id_map.data();
+}
+
+size_t vsb200_dense_last_proto(vsb200_dense* d, uint8_t* buf, size_t cap) {
+  if (!d || !d->last_popped) return 0;
+  encode_proto(*d->last_popped, &d->proto_buf);
+  if (buf && cap) memcpy(buf, d->proto_buf.data(), std::min(cap, d->proto_buf.size()));
+  return d->proto_buf.size();
+}
+
+void vsb200_dense_stats(vsb200_dense* d, double out[9]) {
+  if (d && out) memcpy(out, d->stats, sizeof(double) * 9);
+}
+
+void vsb200_dense_destroy(vsb200_dense* d) { delete d; }
+
+int vsb200_dense_export_halo(vsb200_dense* d, int32_t** dev_prev, int32_t** dev_last, int32_t* max_region_id) {
+  if (!d || !dev_prev || !dev_last || !max_region_id) return VSB200_ERR_INVALID;
+  // valid right after a (non flush) chunk boundary: the id maps that seed the next chunk
+  *dev_prev = d->d_con_ids[0];
+  *dev_last = d->d_con_ids[1];
+  *max_region_id = d->max_region_id;
+  return VSB200_OK;
+}
+
+int vsb200_dense_import_halo(vsb200_dense* d, const int32_t* dev_prev, const int32_t* dev_last, int32_t max_region_id) {
+  if (!d || !dev_prev || !dev_last) return VSB200_ERR_INVALID;
+  if (d->input_frames != 0) { set_error("import_halo must precede the first push"); return VSB200_ERR_INVALID; }
+  set_error("import_halo: pipelined seam (exact semantics) is not built yet; bench.py shards by independent groups");
+  return VSB200_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -255,6 +255,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
     unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
     if (n_live > p.live_cap) n_live = p.live_cap;   // cannot happen: cap = largest bucket
     if (n_live == 0) break;
+    if (first_round && tid == 0) p.stats[4] = n_live;
     if (first_round) {
       // ---- P2a: clusters of this bucket's pending edges ----
       for (unsigned long long i = tid; i < n_live; i += nthr) {
@@ -395,12 +396,22 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
     const unsigned long long s0 = p.bucket_start[b], s1 = p.bucket_start[b + 1];
     if (s1 == s0) continue;
     const unsigned epoch = (unsigned)(*((volatile unsigned long long*)&p.counters[2]));
+    unsigned long long t_bucket = 0;
+    if (p.debug && gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_bucket));
     if (s1 - s0 <= kTailEdges) {
       if (blockIdx.x == 0) run_bucket(p, bbar, threadIdx.x, blockDim.x, b, p.codes + s0, s1 - s0, false, 0u, epoch);
     } else {
       run_bucket(p, gbar, gtid, gn, b, p.codes + s0, s1 - s0, false, 0u, epoch);
     }
     gbar.sync();
+    if (p.debug && gtid == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      p.debug[b * 4 + 0] = t1 - t_bucket;
+      p.debug[b * 4 + 1] = p.stats[0];
+      p.debug[b * 4 + 2] = s1 - s0;
+      p.debug[b * 4 + 3] = p.stats[4];
+    }
   }
 }
 
