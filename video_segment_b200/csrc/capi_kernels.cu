@@ -151,12 +151,14 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.hull = (int*)dalloc(nodes * 32);
     mp.live_a = (uint32_t*)dalloc(max_bucket * 16);
     mp.live_b = (uint32_t*)dalloc(max_bucket * 16);
+    mp.live_aux = (uint32_t*)dalloc(max_bucket * 4);
+    mp.done = (unsigned char*)dalloc(max_bucket);
     mp.live_cap = max_bucket;
     mp.counters = (unsigned long long*)dalloc(16 * 8);
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
     mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc(kNumBuckets * 4 * 8) : nullptr;
     if (mp.debug) cudaMemsetAsync(mp.debug, 0, kNumBuckets * 4 * 8, s);
-    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.counters) {
+    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.live_aux || !mp.done || !mp.counters) {
       set_error("segment_chunk: out of device memory (merge workspace)");
       rc = VSB200_ERR_CUDA;
       break;

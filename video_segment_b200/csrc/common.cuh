@@ -77,7 +77,9 @@ struct MergeParams {
   unsigned long long* acc;         // [nodes][4] fixed-point accumulators: sz, d0, d1, d2
   int* cl;                         // [nodes] scratch cluster union-find
   int* hull;                       // [nodes][8]: min0..2, max0..2, flags, conmin (float bits as int)
-  uint32_t* live_a;                // live edge buffers: triples (code, ru, rv)
+  unsigned char* done;             // [max bucket edges] per-position done flags of the current bucket
+  uint32_t* live_aux;              // [live_cap] cluster root of a live entry (first round of a bucket)
+  uint32_t* live_a;                // live edge buffers: (code, ru, rv, position)
   uint32_t* live_b;
   unsigned long long live_cap;     // in triples
   unsigned long long* counters;    // [8] device counters

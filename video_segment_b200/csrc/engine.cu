@@ -72,7 +72,7 @@ struct vsb200_dense {
   int* d_parent = nullptr; RegionRec* d_rec = nullptr;
   MergeParams mp{};
   unsigned long long live_cap_alloc = 0;
-  int* d_labels = nullptr; int* d_idimg = nullptr; int* d_size_adjust = nullptr;
+  int* d_labels = nullptr; int* d_roots = nullptr; int* d_idimg = nullptr; int* d_size_adjust = nullptr;
   int* d_slice_ids = nullptr; unsigned* d_row_counts = nullptr; unsigned* d_row_offsets = nullptr;
   unsigned* d_total = nullptr;
   RunRec* d_runs = nullptr; size_t runs_cap = 0;
@@ -106,8 +106,8 @@ struct vsb200_dense {
 void vsb200_dense::release() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_bgr); F(d_pre_scratch); F(d_flows); F(d_codes); F(d_bstart); F(d_sort_scratch); F(d_parent); F(d_rec);
-  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.counters);
-  F(d_labels); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
+  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_aux); F(mp.done); F(mp.counters);
+  F(d_labels); F(d_roots); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
   F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
   F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
   for (auto p : d_frames) F(p);
@@ -167,6 +167,7 @@ int vsb200_dense::init() {
   ENG_RC(launch_init_hull(mp.hull, (long long)nodes, stream));
   ENG_CUDA(cudaMalloc(&d_labels, nodes * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_idimg, nodes * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_roots, nodes * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_size_adjust, (nodes + 1) * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_slice_ids, max_slots * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_row_counts, (size_t)max_slots * h * sizeof(unsigned)));
@@ -452,8 +453,12 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     if (mp.live_a) cudaFree(mp.live_a);
     if (mp.live_b) cudaFree(mp.live_b);
     live_cap_alloc = max_bucket + max_bucket / 4;
+    if (mp.done) cudaFree(mp.done);
+    if (mp.live_aux) cudaFree(mp.live_aux);
     ENG_CUDA(cudaMalloc(&mp.live_a, live_cap_alloc * 16));
     ENG_CUDA(cudaMalloc(&mp.live_b, live_cap_alloc * 16));
+    ENG_CUDA(cudaMalloc(&mp.live_aux, live_cap_alloc * 4));
+    ENG_CUDA(cudaMalloc(&mp.done, live_cap_alloc));
   }
   // ---------------- merge ----------------
   mp.w = w; mp.h = h; mp.slots = slots; mp.min_region_size = min_region_size;
@@ -471,6 +476,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   const size_t nodes = (size_t)n * slots;
   ENG_RC(launch_flatten(d_parent, nullptr, d_labels, (long long)nodes, stream));
   ENG_CUDA(cudaMemcpyAsync(d_idimg, d_labels, nodes * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  ENG_CUDA(cudaMemcpyAsync(d_roots, d_labels, nodes * sizeof(int), cudaMemcpyDeviceToDevice, stream));
   ENG_CUDA(cudaMemsetAsync(d_size_adjust, 0, (nodes + 1) * sizeof(int), stream));
   std::vector<int> slice_ids;
   for (int s = 0; s < slots; ++s) if (!(constrained_chunk && s == 0)) slice_ids.push_back(s);
@@ -590,7 +596,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     ENG_CUDA(cudaMemcpyAsync(d_runs, relabel.data(), sizeof(RunRec) * relabel.size(), cudaMemcpyHostToDevice, stream));
     ENG_RC(launch_relabel(d_runs, (int)relabel.size(), w, h, d_labels, stream));
   }
-  ENG_RC(launch_neighbor_pairs(d_labels, w, h, slots, use_flow ? d_flows : nullptr, constrained_chunk ? 1 : 0,
+  ENG_RC(launch_neighbor_pairs(d_roots, d_labels, w, h, slots, use_flow ? d_flows : nullptr, constrained_chunk ? 1 : 0,
                                d_pair_table, pair_table_cap, d_pairs, d_pair_count, pairs_cap, stream));
   unsigned long long n_pairs = 0;
   ENG_CUDA(cudaMemcpyAsync(&n_pairs, d_pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));

@@ -30,7 +30,8 @@ namespace cg = cooperative_groups;
 namespace vsb {
 
 constexpr uint32_t kDone = 0xFFFFFFFFu;
-constexpr unsigned kTailEdges = 4096;     // <= this many pending edges: block 0 finishes the bucket
+constexpr unsigned kTailEdges = 4096;     // <= this many edges: block 0 runs the whole bucket
+constexpr unsigned long long kSerialSwitch = 256;   // grid round progress below this -> serial window mode
 constexpr int kMergeThreads = 256;
 constexpr double kFix = 4294967296.0;     // 2^32 fixed point for descriptor sums
 
@@ -207,55 +208,256 @@ __device__ __forceinline__ void acc_fold(const MergeParams& p, int root) {
   store_rec(&p.rec[root], R);
 }
 
-// counters: [0] live count of buffer A, [1] of buffer B, [2] round epoch
-// live entry = 4 words: code, ru, rv, cluster root
-template <class Bar>
-__device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, const unsigned nthr, const int b,
-                           const uint32_t* src_codes, unsigned long long src_n, bool p1_done_in,
-                           unsigned buf_in, unsigned epoch_in) {
+// ---------------------------------------------------------------------------------------------
+// Serial window mode.  When the grid-wide rounds stop making progress (a long dependency chain:
+// one region growing edge by edge in reference order) block 0 finishes the chain alone: it keeps
+// the kWin smallest pending edges of the bucket (in reference order) in shared memory and runs
+// the same reservation rounds on them behind __syncthreads, with the reservations in a shared
+// hash table.  A window holds every earlier pending edge of each of its edges, so owning both
+// roots inside the window is again "next edge in reference order" -- exact, ~2 us per round.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWin = 512;
+constexpr int kHash = 2048;
+
+struct SerialShared {
+  uint32_t code[kWin], pos[kWin], ru[kWin], rv[kWin];
+  unsigned hkey[kHash], hval[kHash];
+  unsigned warp_cnt[8];
+  int wn, taken, commits;
+  unsigned long long cursor, next_cursor;
+};
+
+__device__ __forceinline__ unsigned hash_slot(unsigned root) { return (root * 2654435761u) >> 21; }   // 11 bits
+__device__ __forceinline__ void hash_min(SerialShared& S, unsigned root, unsigned val) {
+  unsigned slot = hash_slot(root);
+  while (true) {
+    const unsigned k = atomicCAS(&S.hkey[slot], 0u, root + 1u);
+    if (k == 0u || k == root + 1u) { atomicMin(&S.hval[slot], val); return; }
+    slot = (slot + 1u) & (kHash - 1);
+  }
+}
+__device__ __forceinline__ unsigned hash_get(const SerialShared& S, unsigned root) {
+  unsigned slot = hash_slot(root);
+  while (true) {
+    const unsigned k = S.hkey[slot];
+    if (k == root + 1u) return S.hval[slot];
+    if (k == 0u) return 0xFFFFFFFFu;
+    slot = (slot + 1u) & (kHash - 1);
+  }
+}
+
+// block-wide exclusive scan of a 0/1 flag over 256 threads; returns rank, total via smem
+__device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsigned* total) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) S.warp_cnt[wid] = __popc(m);
+  __syncthreads();
+  unsigned base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
+  __syncthreads();
+  *total = tot;
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// Returns true when the bucket is finished, false when the window became productive again
+// (many commits per round: hand back to the grid-wide rounds).
+__device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b, const uint32_t* codes,
+                              const unsigned long long n_edges) {
+  const float inv_scale = (float)(1.0 / (double)bucket_scale());
+  const float edge_w = (float)b * inv_scale;
+  const int mins = p.min_region_size;
+  const int tid = threadIdx.x;
+  if (tid == 0) { S.wn = 0; S.cursor = 0; }
+  for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  unsigned long long rounds = 0;
+  int productive = 0;
+  while (true) {
+    // ---- refill the window with the next pending edges in reference order ----
+    while (true) {
+      const int wn = S.wn;
+      const unsigned long long cur = S.cursor;
+      if (wn >= kWin || cur >= n_edges) break;
+      const unsigned long long pos = cur + tid;
+      const bool pend = (pos < n_edges) && (p.done[pos] == 0);
+      unsigned total;
+      const unsigned rank = block_rank(S, pend, &total);
+      const unsigned room = (unsigned)(kWin - wn);
+      if (tid == 0) S.next_cursor = cur + kMergeThreads;
+      __syncthreads();
+      if (pend) {
+        if (rank < room) { S.code[wn + rank] = codes[pos]; S.pos[wn + rank] = (uint32_t)pos; }
+        else if (rank == room) S.next_cursor = pos;      // first pending edge that did not fit
+      }
+      __syncthreads();
+      if (tid == 0) { S.wn = wn + (int)min(total, room); S.cursor = S.next_cursor; S.commits = 0; }
+      __syncthreads();
+    }
+    const int wn = S.wn;
+    if (wn == 0) return true;
+    if (tid == 0) S.commits = 0;
+    // ---- A: roots, inert edges, reservations (window index == reference order) ----
+    for (int i = tid; i < wn; i += kMergeThreads) {
+      const uint32_t code = S.code[i];
+      int u, v;
+      decode_edge(p, code, u, v);
+      const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+      bool drop = (ru == rv);
+      if (!drop) {
+        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+        const bool both_con = (A.con >= 0 && B.con >= 0);
+        drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+      }
+      if (drop) {
+        p.done[S.pos[i]] = 1;
+        S.code[i] = kDone;
+        S.ru[i] = 0xFFFFFFFFu; S.rv[i] = 0xFFFFFFFFu;
+      } else {
+        S.ru[i] = (uint32_t)ru; S.rv[i] = (uint32_t)rv;
+        hash_min(S, (unsigned)ru, (unsigned)i);
+        hash_min(S, (unsigned)rv, (unsigned)i);
+      }
+    }
+    __syncthreads();
+    // ---- B: commit ----
+    for (int i = tid; i < wn; i += kMergeThreads) {
+      if (S.code[i] == kDone) continue;
+      const int ru = (int)S.ru[i], rv = (int)S.rv[i];
+      const bool own_u = hash_get(S, (unsigned)ru) == (unsigned)i, own_v = hash_get(S, (unsigned)rv) == (unsigned)i;
+      bool done = false;
+      if (own_u && own_v) {
+        exec_strict(p, ru, rv, edge_w, p.stats);
+        done = true;
+      } else if (own_u || own_v) {
+        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+        if (own_v && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
+        else if (own_u && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+      }
+      if (done) {
+        p.done[S.pos[i]] = 1;
+        S.code[i] = kDone;
+        atomicAdd(&S.commits, 1);
+      }
+    }
+    __syncthreads();
+    // ---- C: fold bulk contributions, clear the hash, compact the window (stable) ----
+    for (int i = tid; i < wn; i += kMergeThreads) {
+      if (S.ru[i] == 0xFFFFFFFFu) continue;
+      acc_fold(p, (int)S.ru[i]);
+      acc_fold(p, (int)S.rv[i]);
+    }
+    for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; }
+    // each thread owns window entries [2*tid, 2*tid+1]
+    uint32_t c0 = kDone, c1 = kDone, p0 = 0, p1 = 0;
+    const int i0 = 2 * tid, i1 = 2 * tid + 1;
+    if (i0 < wn) { c0 = S.code[i0]; p0 = S.pos[i0]; }
+    if (i1 < wn) { c1 = S.code[i1]; p1 = S.pos[i1]; }
+    const unsigned k0 = (c0 != kDone) ? 1u : 0u, k1 = (c1 != kDone) ? 1u : 0u;
+    // scan of per-thread keep counts (0..2): two flag scans
+    unsigned tot0, tot1;
+    const unsigned r0 = block_rank(S, k0 != 0, &tot0);
+    const unsigned r1 = block_rank(S, k1 != 0, &tot1);
+    // stable order: entry 2t precedes 2t+1 precedes 2(t+1): rank = (#kept among even idx < 2t) + (#kept among odd idx < 2t)
+    // r0 counts kept even entries of threads < tid; r1 counts kept odd entries of threads < tid.
+    const unsigned dst0 = r0 + r1;
+    const unsigned dst1 = r0 + r1 + k0;
+    const int commits = S.commits;
+    __syncthreads();
+    if (k0) { S.code[dst0] = c0; S.pos[dst0] = p0; }
+    if (k1) { S.code[dst1] = c1; S.pos[dst1] = p1; }
+    if (tid == 0) S.wn = (int)(tot0 + tot1);
+    __syncthreads();
+    ++rounds;
+    if (tid == 0 && (rounds & 1023ull) == 0) atomicAdd(&p.stats[0], 1024ull);
+    // productive again? (more than a quarter of the window committed for several rounds)
+    productive = (commits * 4 >= kWin) ? productive + 1 : 0;
+    if (productive >= 4 && S.cursor < n_edges) {
+      // hand the bucket back: the window's edges stay pending (done flags tell)
+      if (tid == 0) atomicAdd(&p.stats[0], rounds & 1023ull);
+      return false;
+    }
+    if (S.wn == 0 && S.cursor >= n_edges) {
+      if (tid == 0) atomicAdd(&p.stats[0], rounds & 1023ull);
+      return true;
+    }
+  }
+}
+
+// counters: [0] live count of buffer A, [1] of buffer B, [2] round epoch, [3] bucket finished flag
+// live entry = 4 words: code, ru, rv, position in the bucket; live_aux[slot] = cluster root (round 0)
+template <class Bar, bool kIsGrid>
+__device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, const unsigned tid, const unsigned nthr,
+                           const int b, const uint32_t* codes, const unsigned long long n_edges, unsigned epoch) {
   const float inv_scale = (float)(1.0 / (double)bucket_scale());   // segmentation_graph.h:348
   const float edge_w = (float)b * inv_scale;
   const bool force_bucket = edge_w < p.force_merge_weight;
   const float safe_thr = (force_bucket ? 0.2f : 0.05f) * 0.999f;
   const int mins = p.min_region_size;
-  unsigned buf = buf_in;            // index of the buffer P1 writes to
-  unsigned epoch = epoch_in;
-  bool from_codes = (src_codes != nullptr);
-  bool first_round = from_codes;
-  bool p1_done = p1_done_in;
-  unsigned long long n_src = src_n;
+  unsigned buf = 0;                 // index of the buffer P1 writes to
+  bool first_round = true;
+  unsigned long long n_src = n_edges, prev_live = n_edges;
+  // done flags of this bucket
+  for (unsigned long long i = tid; i < n_edges; i += nthr) p.done[i] = 0;
+  bar.sync();
   while (true) {
     uint32_t* dst = buf ? p.live_b : p.live_a;
     const uint32_t* src = buf ? p.live_a : p.live_b;
     unsigned long long* dst_cnt = &p.counters[buf];
     const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - epoch)) << 32;
-    if (!p1_done) {
-      // ---- P1: find roots, drop inert edges, reserve ----
-      for (unsigned long long i = tid; i < n_src; i += nthr) {
-        const uint32_t code = from_codes ? src_codes[i] : src[i * 4];
-        if (code == kDone) continue;
-        int u, v;
-        decode_edge(p, code, u, v);
-        const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-        if (ru == rv) continue;
+    // ---- P1: find roots, drop inert edges, reserve ----
+    for (unsigned long long i = tid; i < n_src; i += nthr) {
+      uint32_t code, pos;
+      if (first_round) { code = codes[i]; pos = (uint32_t)i; }
+      else { const uint4 e = reinterpret_cast<const uint4*>(src)[i]; code = e.x; pos = e.w; }
+      if (code == kDone || p.done[pos]) continue;
+      int u, v;
+      decode_edge(p, code, u, v);
+      const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+      bool drop = (ru == rv);
+      if (!drop) {
         const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
         const bool both_con = (A.con >= 0 && B.con >= 0);
-        if (both_con && A.con != B.con) continue;                       // kept for ever
-        if (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins) continue;   // inert
-        const unsigned long long slot = atomicAdd(dst_cnt, 1ull);
-        if (slot < p.live_cap) {
-          reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, 0u);
-          atomicMin(&p.res[ru], key_hi | code);
-          atomicMin(&p.res[rv], key_hi | code);
-        }
+        drop = (both_con && A.con != B.con)                                   // kept for ever
+               || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);   // inert
       }
-      bar.sync();
+      if (drop) { p.done[pos] = 1; continue; }
+      const unsigned long long slot = atomicAdd(dst_cnt, 1ull);
+      if (slot < p.live_cap) {
+        reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
+        atomicMin(&p.res[ru], key_hi | code);
+        atomicMin(&p.res[rv], key_hi | code);
+      }
     }
-    p1_done = false;
+    bar.sync();
     unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
     if (n_live > p.live_cap) n_live = p.live_cap;   // cannot happen: cap = largest bucket
     if (n_live == 0) break;
     if (first_round && tid == 0) p.stats[4] = n_live;
+    // ---- chain regime: let block 0 finish (or advance) the bucket in serial window mode ----
+    if (!first_round && prev_live - n_live < kSerialSwitch) {
+      if (kIsGrid) {
+        if (blockIdx.x == 0) {
+          const bool fin = serial_rounds(p, S, b, codes, n_edges);
+          if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+        }
+      } else {
+        const bool fin = serial_rounds(p, S, b, codes, n_edges);
+        if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+      }
+      bar.sync();
+      const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
+      if (finished) break;
+      // productive again: next grid round re-reads this round's list (done flags filter it)
+      if (tid == 0) p.counters[buf ^ 1] = 0ull;
+      bar.sync();
+      n_src = n_live;
+      prev_live = ~0ull >> 1;       // force at least one grid round
+      buf ^= 1;
+      ++epoch;
+      continue;
+    }
+    prev_live = n_live;
     if (first_round) {
       // ---- P2a: clusters of this bucket's pending edges ----
       for (unsigned long long i = tid; i < n_live; i += nthr) {
@@ -267,7 +469,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
       for (unsigned long long i = tid; i < n_live; i += nthr) {
         const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
         const int c = cl_find(p.cl, (int)e.y);
-        reinterpret_cast<uint4*>(dst)[i].w = (uint32_t)c;
+        p.live_aux[i] = (uint32_t)c;
         int* hl = p.hull + (size_t)c * 8;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -278,21 +480,18 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
           atomicMin(&hl[2], __float_as_int(R.d2)); atomicMax(&hl[5], __float_as_int(R.d2));
           if (R.fin) atomicOr(&hl[6], 1);
           if (R.con >= 0) { atomicMin(&hl[7], R.con); atomicOr(&hl[6], 2); }
-          else atomicOr(&hl[6], 4);
         }
       }
       bar.sync();
-      // ---- P2c: merge safe clusters in bulk ----
+      // ---- P2c: which clusters are safe (any objecting edge makes its cluster ordered) ----
       for (unsigned long long i = tid; i < n_live; i += nthr) {
         const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        const int c = (int)e.w;
+        const int c = (int)p.live_aux[i];
         int* hl = p.hull + (size_t)c * 8;
         const int flags = hl[6];
         bool safe = (flags & 1) == 0;
         if (safe && (flags & 2)) {
-          // constrained members: all must carry one id -> compare min with max via the records
-          // (max is tracked through the cluster root's own constraint below); use min only and
-          // verify both endpoints agree.
+          // constrained members must all carry one id: every root is an endpoint of some edge
           const RegionRec A = load_rec(&p.rec[(int)e.y]), B = load_rec(&p.rec[(int)e.z]);
           const int cmin = hl[7];
           if ((A.con >= 0 && A.con != cmin) || (B.con >= 0 && B.con != cmin)) safe = false;
@@ -304,12 +503,13 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
           const float diam = sqrtf((dx * dx + dy * dy + dz * dz) * (1.0f / 3.0f));
           safe = diam < safe_thr;
         }
-        if (!safe) atomicOr(&hl[6], 8);   // one objecting edge makes the whole cluster ordered
+        if (!safe) atomicOr(&hl[6], 8);
       }
       bar.sync();
+      // ---- P2d: merge safe clusters in bulk ----
       for (unsigned long long i = tid; i < n_live; i += nthr) {
         const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        const int c = (int)e.w;
+        const int c = (int)p.live_aux[i];
         const int* hl = p.hull + (size_t)c * 8;
         if (hl[6] & 8) continue;             // unsafe cluster -> ordered rounds
 #pragma unroll
@@ -324,6 +524,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
           }
         }
         reinterpret_cast<uint4*>(dst)[i].x = kDone;
+        p.done[e.w] = 1;
       }
       bar.sync();
     }
@@ -332,7 +533,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
       const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
       const int ru = (int)e.y, rv = (int)e.z;
       if (first_round) {
-        const int c = (int)e.w;
+        const int c = (int)p.live_aux[i];
         int* hl = p.hull + (size_t)c * 8;
         reinterpret_cast<int4*>(hl)[0] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
         reinterpret_cast<int4*>(hl)[1] = make_int4(0, 0, 0, 0x7f7f7f7f);
@@ -342,22 +543,19 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
       if (e.x == kDone) continue;
       const unsigned long long key = key_hi | e.x;
       const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
+      bool done = false;
       if (own_u && own_v) {
         exec_strict(p, ru, rv, edge_w, p.stats);
-        reinterpret_cast<uint4*>(dst)[i].x = kDone;
-        continue;
+        done = true;
+      } else if (own_u || own_v) {
+        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+        // x = the side this edge is the next edge of; hub = finalised region of >= min size
+        if (own_v && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
+        else if (own_u && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
       }
-      if (!own_u && !own_v) continue;
-      const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-      // x = the side this edge is the next edge of; hub = finalised region of >= min size
-      if (own_v && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) {
-        p.parent[rv] = ru;
-        acc_add(p.acc, ru, B);
+      if (done) {
         reinterpret_cast<uint4*>(dst)[i].x = kDone;
-      } else if (own_u && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) {
-        p.parent[ru] = rv;
-        acc_add(p.acc, rv, A);
-        reinterpret_cast<uint4*>(dst)[i].x = kDone;
+        p.done[e.w] = 1;
       }
     }
     bar.sync();
@@ -366,7 +564,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
       const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
       acc_fold(p, (int)e.y);
       acc_fold(p, (int)e.z);
-      if (first_round) acc_fold(p, (int)e.w);
+      if (first_round) acc_fold(p, (int)p.live_aux[i]);
     }
     if (tid == 0) {
       p.counters[buf ^ 1] = 0ull;          // the other buffer becomes the next destination
@@ -375,7 +573,6 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
     bar.sync();
     // next round reads what this round wrote
     n_src = n_live;
-    from_codes = false;
     first_round = false;
     buf ^= 1;
     ++epoch;
@@ -384,10 +581,12 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, const unsigned tid, c
     p.counters[0] = 0ull;
     p.counters[1] = 0ull;
     p.counters[2] = (unsigned long long)(epoch + 1);
+    p.counters[3] = 0ull;
   }
 }
 
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
+  __shared__ SerialShared S;
   GridBar gbar{cg::this_grid()};
   BlockBar bbar;
   const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -399,9 +598,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
     unsigned long long t_bucket = 0;
     if (p.debug && gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_bucket));
     if (s1 - s0 <= kTailEdges) {
-      if (blockIdx.x == 0) run_bucket(p, bbar, threadIdx.x, blockDim.x, b, p.codes + s0, s1 - s0, false, 0u, epoch);
+      if (blockIdx.x == 0) run_bucket<BlockBar, false>(p, bbar, S, threadIdx.x, blockDim.x, b, p.codes + s0, s1 - s0, epoch);
     } else {
-      run_bucket(p, gbar, gtid, gn, b, p.codes + s0, s1 - s0, false, 0u, epoch);
+      run_bucket<GridBar, true>(p, gbar, S, gtid, gn, b, p.codes + s0, s1 - s0, epoch);
     }
     gbar.sync();
     if (p.debug && gtid == 0) {

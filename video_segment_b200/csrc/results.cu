@@ -250,7 +250,7 @@ __device__ __forceinline__ void pair_insert(unsigned long long* table, unsigned 
   }
 }
 
-__global__ void neighbor_pairs_kernel(const int* __restrict__ labels, int w, int h, int slots,
+__global__ void neighbor_pairs_kernel(const int* __restrict__ roots, const int* __restrict__ labels, int w, int h, int slots,
                                       const float* __restrict__ flows, int virtual_slot0,
                                       unsigned long long* __restrict__ table, unsigned cap_mask,
                                       unsigned long long* __restrict__ out, unsigned long long* __restrict__ out_count,
@@ -261,15 +261,22 @@ __global__ void neighbor_pairs_kernel(const int* __restrict__ labels, int w, int
        i += (long long)gridDim.x * blockDim.x) {
     const int slot = (int)(i / n), pix = (int)(i % n);
     const int x = pix % w, y = pix / w;
-    const int la = labels[i];
-    int last = la;
+    // An edge contributes a neighbour pair iff its endpoints ended in different union-find
+    // regions (edges inside one region were dropped or merged, segmentation_graph.h:375-440);
+    // the pair is reported on the labels after the tube split (EnforceSpatialConnectedness).
+    const int ra = roots[i], la = labels[i];
+    int last = -2;
+#define VSB_PAIR(J)                                                                         \
+    { const long long j_ = (J); const int rb = roots[j_];                                   \
+      if (rb != ra) { const int lb = labels[j_];                                            \
+        if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } } }
     // spatial edges R, B, BL, BR (virtual slots have none, dense_segmentation_graph.h:327-367)
     if (!(virtual_slot0 && slot == 0)) {
-      if (x + 1 < w) { const int lb = labels[i + 1]; if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } }
+      if (x + 1 < w) VSB_PAIR(i + 1)
       if (y + 1 < h) {
-        { const int lb = labels[i + w]; if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } }
-        if (x > 0) { const int lb = labels[i + w - 1]; if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } }
-        if (x + 1 < w) { const int lb = labels[i + w + 1]; if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } }
+        VSB_PAIR(i + w)
+        if (x > 0) VSB_PAIR(i + w - 1)
+        if (x + 1 < w) VSB_PAIR(i + w + 1)
       }
     }
     if (slot > 0) {
@@ -279,24 +286,24 @@ __global__ void neighbor_pairs_kernel(const int* __restrict__ labels, int w, int
         px = max(0, min(w - 1, (int)((float)x + f[0])));
         py = max(0, min(h - 1, (int)((float)y + f[1])));
       }
-      const int* prev = labels + (size_t)(slot - 1) * n;
+      const long long pbase = (long long)(slot - 1) * n;
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
           const int xx = px + dx, yy = py + dy;
           if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
-          const int lb = prev[yy * w + xx];
-          if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; }
+          VSB_PAIR(pbase + (long long)yy * w + xx)
         }
     }
+#undef VSB_PAIR
   }
 }
 
-int launch_neighbor_pairs(const int* labels, int w, int h, int slots, const float* flows, int virtual_slot0,
+int launch_neighbor_pairs(const int* roots, const int* labels, int w, int h, int slots, const float* flows, int virtual_slot0,
                           unsigned long long* table, unsigned table_cap_pow2, unsigned long long* out,
                           unsigned long long* out_count, unsigned long long out_cap, cudaStream_t s) {
   VSB_CUDA_OK(cudaMemsetAsync(table, 0xff, sizeof(unsigned long long) * (size_t)table_cap_pow2, s));
   VSB_CUDA_OK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), s));
-  neighbor_pairs_kernel<<<148 * 8, 256, 0, s>>>(labels, w, h, slots, flows, virtual_slot0, table, table_cap_pow2 - 1,
+  neighbor_pairs_kernel<<<148 * 8, 256, 0, s>>>(roots, labels, w, h, slots, flows, virtual_slot0, table, table_cap_pow2 - 1,
                                                out, out_count, out_cap);
   VSB_CUDA_OK(cudaGetLastError());
   return 0;

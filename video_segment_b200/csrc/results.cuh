@@ -15,7 +15,7 @@ int launch_rle_write(const int* labels, int w, int h, const int* dev_slice_ids, 
 int launch_gather_region_info(const int* ids, int n, const RegionRec* rec, const int* size_adjust, int2* out,
                               cudaStream_t s);
 int launch_relabel(const RunRec* runs, int n, int w, int h, int* node_labels, cudaStream_t s);
-int launch_neighbor_pairs(const int* labels, int w, int h, int slots, const float* flows, int virtual_slot0,
+int launch_neighbor_pairs(const int* roots, const int* labels, int w, int h, int slots, const float* flows, int virtual_slot0,
                           unsigned long long* table, unsigned table_cap_pow2, unsigned long long* out,
                           unsigned long long* out_count, unsigned long long out_cap, cudaStream_t s);
 int launch_fill_i32(int* p, int value, long long n, cudaStream_t s);
