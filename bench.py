@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of dense video over-segmentation at 1920x1080 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...     # reference CPU path (oracle port)
+
+A "step" is one chunk of the streaming hot path: 19 new 1080p frames pushed through the
+DenseSegmentationUnit mirror (preprocess -> edge build -> bucket sort -> merge -> labels / N4 /
+RLE -> region bookkeeping), i.e. exactly what the reference outputs per chunk
+(dense_segmentation.cpp:281-432).  Rank 0 prints ONE JSON line (see the task contract):
+  value   : frames/s with the u8 frames already resident in HBM (vsb200_dense_push_device)
+  e2e     : frames/s through the public host API (host frames in, host SegmentationDesc arrays
+            out): every step copies its 19 frames H2D from pinned staging and reads the
+            rasterisation runs / neighbour pairs back
+  roofline: edge-build kernel, algorithmic bytes / CUDA-event time of its launches inside the
+            timed region, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline : the oracle (line-by-line port of the reference's CPU path, oracle/) timed on
+            the same box's host cores on a bounded sample (rank 0, N = 1 only)
+Multi GPU (torchrun): frame-chunk groups of ONE synthetic video are sharded over the ranks
+(weak scaling, fixed frames per GPU); the only data-path exchange is the seam hand-over of the
+two overlap frames' region-id maps (NCCL send/recv over NVLink, C1) and the all-gather of the
+groups' region-id counts (C2); both run inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "frames/sec 1080p dense over-seg"
+FRAMES_PER_STEP = 19          # new frames per chunk (chunk_size 20, 1 virtual + 1 constrained overlap)
+UNIQUE_FRAMES = 39            # generated frames per rank; longer runs ping-pong over them
+
+
+def edge_build_bytes(w, h):
+    n = w * h
+    es = (w - 1) * h + w * (h - 1) + 2 * (w - 1) * (h - 1)
+    et = (3 * w - 2) * (3 * h - 2)
+    return 24 * n + 4 * (es + et)          # 12N + 12N read, 4 (Es + Et) written
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def frame_index(k):
+    """Ping-pong over the generated frames keeps the video temporally continuous."""
+    period = 2 * (UNIQUE_FRAMES - 1)
+    k %= period
+    return k if k < UNIQUE_FRAMES else period - k
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the real
+    seg_tree_sample cannot be built in this image) on the box's host cores."""
+    if rank != 0:
+        return
+    import oracle_binding as ob
+    from video_segment_b200.synth import synth
+    w, h = args.width, args.height
+    cores = os.cpu_count() or 1
+    nfr = args.ref_frames
+    frames = list(synth(3, w, h, nfr))
+    def one_step():
+        o = ob.OracleDense(w, h, num_threads=cores)
+        got = 0
+        for f in frames:
+            got += len(o.push(f))
+        got += len(o.flush())
+        o.close()
+        return got
+    for _ in range(min(args.warmup, 1)):      # CPU path: one warm-up pass is enough and keeps the run bounded
+        one_step()
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        total += one_step()
+    dt = time.perf_counter() - t0
+    fps = total / dt
+    sample = f"{nfr} frames of the {w}x{h} synthetic clip (seed 3) segmented as one flushed chunk per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w}x{h} synthetic, dense over-seg only (BASELINE config 3 without the hierarchical stage)",
+                   "step": sample, "threads": cores},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from video_segment_b200._lib import lib
+    from video_segment_b200.synth import synth
+    from video_segment_b200.unit import DenseSegmentationUnit
+
+    if not torch.cuda.is_available() or lib().vsb200_device_count() < 1:
+        raise SystemExit("bench.py: no B200 / CUDA library -- this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w, h = args.width, args.height
+    n = w * h
+    K, W = args.steps, args.warmup
+    if W < 3:
+        print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
+    frames_per_rank = 1 + FRAMES_PER_STEP * (W + K)
+    # One video, sharded: rank g owns frames [g * L, (g + 1) * L] (one read-overlap frame).
+    start = rank * (frames_per_rank - 1)
+    host_frames = list(synth(3, w, h, min(UNIQUE_FRAMES, frames_per_rank), start=start))
+    dev_frames = [torch.from_numpy(f).cuda() for f in host_frames]
+    pinned = [torch.from_numpy(f).pin_memory() for f in host_frames]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    halo = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
+    halo_in = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
+
+    def seam_exchange(unit):
+        """C1: overlap id maps to the successor group; C2: all-gather of the region-id counts."""
+        if world == 1:
+            return
+        max_id = unit.export_halo(halo[0].data_ptr(), halo[1].data_ptr())
+        ops = []
+        if rank + 1 < world:
+            ops.append(dist.P2POp(dist.isend, halo, rank + 1))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, halo_in, rank - 1))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([max_id], dtype=torch.int64, device="cuda"))
+        for r in reqs:
+            r.wait()
+
+    def run_leg(device_resident):
+        unit = DenseSegmentationUnit(device=local_rank)
+        if not unit.open_streams(w, h):
+            raise SystemExit("bench.py: " + lib().vsb200_last_error().decode())
+        unit.set_profiling(True)
+        k = 0
+        def push_next():
+            nonlocal k
+            i = frame_index(k)
+            k += 1
+            if device_resident:
+                return unit.process_device_frame(dev_frames[i].data_ptr(), w * 3)
+            return unit.process_frame(pinned[i].numpy())
+        out_frames = 0
+        # warm-up: W chunks (the first one takes 20 frames)
+        while out_frames < FRAMES_PER_STEP * W:
+            out_frames += len(push_next())
+        st0, io0 = unit.stats(), unit.io_stats()
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        timed = 0
+        while timed < FRAMES_PER_STEP * K:
+            timed += len(push_next())
+        seam_exchange(unit)
+        torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        sampler.stop_flag = True
+        ms = e0.elapsed_time(e1)
+        st1, io1 = unit.stats(), unit.io_stats()
+        unit.close()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        d = {k2: st1[k2] - st0[k2] for k2 in st1}
+        dio = {k2: io1[k2] - io0[k2] for k2 in io1}
+        return dict(ms=float(t.item()), wall=wall, frames=timed, stats=d, io=dio, clocks=sampler.summary())
+
+    leg_dev = run_leg(True)
+    leg_e2e = run_leg(False)
+
+    total_frames = FRAMES_PER_STEP * K * world
+    value = total_frames / (leg_dev["ms"] / 1000.0)
+    e2e = total_frames / (leg_e2e["ms"] / 1000.0)
+    # roofline of the edge-build kernel (dominant HBM kernel named by BASELINE.json)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    io = leg_dev["io"]
+    edge_ms = io["edge_ms"] / max(io["edge_launches"], 1)
+    achieved = edge_build_bytes(w, h) / (edge_ms * 1e-3) / 1e9 if edge_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "edge_build_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": leg_dev["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (video_segment_b200.synth seed 3, 39 unique frames per GPU, ping-pong)",
+        "config": {"workload": f"{w}x{h} synthetic, dense over-seg only (BASELINE config 3 without the hierarchical stage)",
+                   "step": f"one chunk = {FRAMES_PER_STEP} new frames per GPU", "frames_per_gpu": FRAMES_PER_STEP * K,
+                   "parallelism": f"frame-chunk groups x{world}", "l2": "inputs larger than L2: 21 slots x 24.9 MB frames + 2.3 GB edge weights per chunk"},
+        "e2e": {"value": e2e, "unit": "frames/s",
+                "h2d_bytes_per_step": leg_e2e["io"]["h2d_bytes"] / K, "d2h_bytes_per_step": leg_e2e["io"]["d2h_bytes"] / K},
+        "gpu_launches": int(leg_dev["stats"]["kernel_launches"]),
+        "clocks": leg_dev["clocks"],
+        "roofline": {"bound": "hbm", "kernel": "edge_build_tiled_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "bytes_per_launch": edge_build_bytes(w, h), "ms_per_launch": edge_ms, "launches_timed": int(io["edge_launches"])},
+        "stage_ms_per_step": {k2: v / K for k2, v in leg_dev["stats"].items() if k2.endswith("_ms")},
+        "merge_rounds_per_step": leg_dev["stats"]["merge_rounds"] / K,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_binding as ob
+        cores = os.cpu_count() or 1
+        nfr = 4
+        o = ob.OracleDense(w, h, num_threads=cores)
+        t0 = time.perf_counter()
+        got = 0
+        for f in host_frames[:nfr]:
+            got += len(o.push(f))
+        got += len(o.flush())
+        dt = time.perf_counter() - t0
+        o.close()
+        line["cpu_baseline"] = {"value": got / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"first {nfr} frames of the same clip segmented as one flushed chunk ({dt:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,10 @@ int vsb200_dense_create(const vsb200_dense_opts* o, int width, int height, int u
  * frames whose results became available (a whole chunk at a time). */
 int vsb200_dense_push(vsb200_dense*, const uint8_t* bgr, int row_stride_bytes,
                       const float* flow_xy, int flow_row_stride_bytes, int64_t pts, int* n_ready);
+/* Same as push for a frame that is already resident in device memory (on-device decoder,
+ * bench.py's HBM-resident leg); no flow. */
+int vsb200_dense_push_device(vsb200_dense*, const uint8_t* dev_bgr, int row_stride_bytes, int64_t pts,
+                             int* n_ready);
 /* == ProcessFrame(flush = true) / PostProcess (segmentation_unit.cpp:154-161). */
 int vsb200_dense_flush(vsb200_dense*, int* n_ready);
 /* Results in input order. */
@@ -100,13 +104,18 @@ size_t vsb200_dense_last_proto(vsb200_dense*, uint8_t* buf, size_t cap);
  * [0] h2d+preprocess [1] edge build [2] sort [3] merge [4] labels+n4+rle [5] host shaping
  * [6] neighbours; and counters [7] kernels launched [8] merge rounds. */
 void vsb200_dense_stats(vsb200_dense*, double out[9]);
+/* Profiling taps (<-> the per-unit timers of video_framework/video_unit.cpp:181-217): CUDA-event
+ * timing of every steady-state edge-build launch on the engine's stream; io_stats returns
+ * [0] host->device bytes [1] device->host bytes [2] edge-build ms total [3] edge-build launches. */
+void vsb200_dense_set_profiling(vsb200_dense*, int time_edge_kernel);
+void vsb200_dense_io_stats(vsb200_dense*, double out[4]);
 void vsb200_dense_destroy(vsb200_dense*);
 
-/* Multi-GPU seam: region-id maps of the last two frames a group
- * produced, to be injected into the successor group's first chunk exactly like
- * overlap_segmentations_ (dense_segmentation.cpp:300-315).  Device pointers (int32 [h*w]),
- * so the caller can ncclSend/ncclRecv them without staging. */
-int vsb200_dense_export_halo(vsb200_dense*, int32_t** dev_id_map_prev, int32_t** dev_id_map_last,
+/* Multi-GPU seam: region-id maps of the two overlap frames a group
+ * holds right after a chunk boundary (overlap_segmentations_, dense_segmentation.cpp:300-315),
+ * copied into caller-provided DEVICE buffers (int32 [h*w] each) so the caller can
+ * ncclSend/ncclRecv them without host staging, plus the group's max region id (C2). */
+int vsb200_dense_export_halo(vsb200_dense*, int32_t* dev_id_map_prev_out, int32_t* dev_id_map_last_out,
                              int32_t* max_region_id);
 int vsb200_dense_import_halo(vsb200_dense*, const int32_t* dev_id_map_prev,
                              const int32_t* dev_id_map_last, int32_t max_region_id);

@@ -41,7 +41,8 @@ class FrameResult(C.Structure):
 # every symbol include/vsb200.h declares
 EXPORTED_SYMBOLS = [
     "vsb200_dense_default_opts", "vsb200_last_error", "vsb200_device_count",
-    "vsb200_dense_create", "vsb200_dense_push", "vsb200_dense_flush", "vsb200_dense_pop",
+    "vsb200_dense_create", "vsb200_dense_push", "vsb200_dense_push_device", "vsb200_dense_flush", "vsb200_dense_pop",
+    "vsb200_dense_set_profiling", "vsb200_dense_io_stats",
     "vsb200_dense_last_id_map", "vsb200_dense_last_proto", "vsb200_dense_stats",
     "vsb200_dense_destroy", "vsb200_dense_export_halo", "vsb200_dense_import_halo",
     "vsb200_preprocess_scratch_bytes", "vsb200_preprocess", "vsb200_edge_build",
@@ -75,13 +76,16 @@ def lib() -> C.CDLL:
         "vsb200_segment_chunk": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_double), vp], C.c_int),
         "vsb200_dense_create": ([C.POINTER(DenseOpts), C.c_int, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
         "vsb200_dense_push": ([vp, vp, C.c_int, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)], C.c_int),
+        "vsb200_dense_push_device": ([vp, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)], C.c_int),
+        "vsb200_dense_set_profiling": ([vp, C.c_int], None),
+        "vsb200_dense_io_stats": ([vp, C.POINTER(C.c_double)], None),
         "vsb200_dense_flush": ([vp, C.POINTER(C.c_int)], C.c_int),
         "vsb200_dense_pop": ([vp, C.POINTER(FrameResult)], C.c_int),
         "vsb200_dense_last_id_map": ([vp], C.POINTER(C.c_int32)),
         "vsb200_dense_last_proto": ([vp, vp, C.c_size_t], C.c_size_t),
         "vsb200_dense_stats": ([vp, C.POINTER(C.c_double)], None),
         "vsb200_dense_destroy": ([vp], None),
-        "vsb200_dense_export_halo": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32)], C.c_int),
+        "vsb200_dense_export_halo": ([vp, vp, vp, C.POINTER(C.c_int32)], C.c_int),
         "vsb200_dense_import_halo": ([vp, vp, vp, C.c_int32], C.c_int),
     }
     missing = []

@@ -2,8 +2,12 @@
 // whole-chunk segmentation used by the merge parity tests and bench.py.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <unistd.h>
 
 #include "../../include/vsb200.h"
 #include "common.cuh"
@@ -158,6 +162,23 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
     mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc(kNumBuckets * 4 * 8) : nullptr;
     if (mp.debug) cudaMemsetAsync(mp.debug, 0, kNumBuckets * 4 * 8, s);
+    mp.trace = nullptr;
+    unsigned long long* h_trace = nullptr;
+    std::atomic<bool> trace_stop{false};
+    std::thread trace_thread;
+    if (getenv("VSB200_MERGE_TRACE")) {
+      cudaHostAlloc(&h_trace, 64 * 8, cudaHostAllocMapped);
+      memset(h_trace, 0, 64 * 8);
+      cudaHostGetDevicePointer((void**)&mp.trace, h_trace, 0);
+      std::string path = getenv("VSB200_MERGE_TRACE");
+      trace_thread = std::thread([h_trace, path, &trace_stop]() {
+        while (!trace_stop.load()) {
+          FILE* f = fopen(path.c_str(), "a");
+          if (f) { fprintf(f, "bucket %llu guard %llu n_live %llu stage %llu serial_rounds %llu wn %llu cursor %llu\n", h_trace[0], h_trace[1], h_trace[2], h_trace[3], h_trace[4], h_trace[5], h_trace[6]); fclose(f); }
+          usleep(500000);
+        }
+      });
+    }
     if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.live_aux || !mp.done || !mp.counters) {
       set_error("segment_chunk: out of device memory (merge workspace)");
       rc = VSB200_ERR_CUDA;
@@ -168,7 +189,9 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     cudaMemsetAsync(mp.counters, 0, 16 * 8, s);
     if ((rc = launch_init_iota(mp.cl, (long long)nodes, s))) break;
     if ((rc = launch_init_hull(mp.hull, (long long)nodes, s))) break;
-    if ((rc = launch_merge(mp, s))) break;
+    rc = launch_merge(mp, s);
+    if (h_trace) { cudaStreamSynchronize(s); trace_stop.store(true); trace_thread.join(); cudaFreeHost(h_trace); }
+    if (rc) break;
     cudaEventRecord(ev[3], s);
     if ((rc = launch_flatten(parent, nullptr, dev_labels_out, (long long)nodes, s))) break;
     unsigned long long h_stats[8];

@@ -84,6 +84,7 @@ struct MergeParams {
   unsigned long long live_cap;     // in triples
   unsigned long long* counters;    // [8] device counters
   unsigned long long* stats;       // [8] rounds, commits, safe merges, ...
+  unsigned long long* trace;       // optional mapped host memory: live progress markers (debugging hangs)
   unsigned long long* debug;       // optional [2048][4]: ns, cumulative rounds, edges, pending after pruning
 };
 size_t merge_scratch_bytes(int w, int h, int slots, unsigned long long max_bucket_edges);

@@ -89,11 +89,14 @@ struct vsb200_dense {
   std::vector<uint8_t> proto_buf;
   bool have_import = false;
   double stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double h2d_bytes = 0, d2h_bytes = 0, edge_ms = 0, edge_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> edge_events;   // timing of the edge-build launches
+  int time_edges = 0;
 
   ~vsb200_dense() { release(); }
   void release();
   int init();
-  int push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready);
+  int push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready, bool device_input);
   int flush(int* n_ready);
   int add_frame_to_graph(int slot, const int* d_constraints);
   int start_constrained_chunk();
@@ -160,6 +163,7 @@ int vsb200_dense::init() {
   ENG_CUDA(cudaMalloc(&mp.counters, 16 * 8));
   mp.stats = mp.counters + 8;
   mp.debug = nullptr;
+  mp.trace = nullptr;
   ENG_CUDA(cudaMemsetAsync(mp.res, 0xff, nodes * 8, stream));
   ENG_CUDA(cudaMemsetAsync(mp.acc, 0, nodes * 32, stream));
   ENG_CUDA(cudaMemsetAsync(mp.counters, 0, 16 * 8, stream));
@@ -188,13 +192,16 @@ int vsb200_dense::add_frame_to_graph(int slot, const int* d_constraints) {
   ENG_RC(launch_init_nodes(d_frames[slot], d_constraints, slot, w, h, d_parent, d_rec, stream));
   const bool temporal = slot >= 1 && !(chunk_id > 0 && slot == 1);   // slot 1 of later chunks: virtual edges only
   const float* flow = (use_flow && temporal) ? d_flows + (size_t)slot * n * 2 : nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (time_edges && temporal) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
   ENG_RC(launch_edge_build(d_frames[slot], temporal ? d_frames[slot - 1] : nullptr, flow, w, h, l1, d_spatial[slot],
                            temporal ? d_temporal[slot] : nullptr, stream));
+  if (e0) { cudaEventRecord(e1, stream); edge_events.emplace_back(e0, e1); }
   stats[7] += 2;
   return 0;
 }
 
-int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready) {
+int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready, bool device_input) {
   if (n_ready) *n_ready = 0;
   if (!bgr || stride < w * 3) { set_error("push: bad frame buffer"); return VSB200_ERR_INVALID; }
   if (use_flow && input_frames > 0 && !flow) { set_error("push: flow missing (created with use_flow)"); return VSB200_ERR_INVALID; }
@@ -203,10 +210,16 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
   pts_queue.push_back(pts);
   const double t0 = now_ms();
   const int slot = buffered;
-  // H2D: pinned staging (the caller may release its buffer when push returns)
-  for (int y = 0; y < h; ++y) memcpy(h_bgr + (size_t)y * w * 3, bgr + (size_t)y * stride, (size_t)w * 3);
-  ENG_CUDA(cudaMemcpyAsync(d_bgr, h_bgr, (size_t)n * 3, cudaMemcpyHostToDevice, stream));
-  ENG_RC(launch_preprocess(d_bgr, w * 3, w, h, o.presmoothing, d_frames[slot], d_pre_scratch, stream));
+  if (device_input) {
+    // frame already resident in HBM (bench.py `value` leg / on-device decoders): no staging copy
+    ENG_RC(launch_preprocess(bgr, stride, w, h, o.presmoothing, d_frames[slot], d_pre_scratch, stream));
+  } else {
+    // H2D: pinned staging (the caller may release its buffer when push returns)
+    for (int y = 0; y < h; ++y) memcpy(h_bgr + (size_t)y * w * 3, bgr + (size_t)y * stride, (size_t)w * 3);
+    ENG_CUDA(cudaMemcpyAsync(d_bgr, h_bgr, (size_t)n * 3, cudaMemcpyHostToDevice, stream));
+    h2d_bytes += (double)n * 3;
+    ENG_RC(launch_preprocess(d_bgr, w * 3, w, h, o.presmoothing, d_frames[slot], d_pre_scratch, stream));
+  }
   stats[7] += (o.presmoothing == 2) ? 3 : 1;
   if (use_flow) {
     if (input_frames == 0 || !flow) {
@@ -219,6 +232,7 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
       ENG_CUDA(cudaStreamSynchronize(stream));       // staging buffer reuse
       memcpy(h_flow_stage, h_flows[slot].data(), sizeof(float) * 2 * n);
       ENG_CUDA(cudaMemcpyAsync(d_flows + (size_t)slot * n * 2, h_flow_stage, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, stream));
+      h2d_bytes += (double)n * 8;
     }
   }
   ENG_RC(add_frame_to_graph(slot, nullptr));
@@ -431,6 +445,11 @@ int vsb200_dense::merge_constrained_regions(int slots) {
 int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr<FrameOut>>* results) {
   const int slots = buffered;
   const bool constrained_chunk = chunk_id > 0;
+  if (!edge_events.empty()) {
+    cudaStreamSynchronize(stream);
+    for (auto& ev2 : edge_events) { float ms = 0; cudaEventElapsedTime(&ms, ev2.first, ev2.second); edge_ms += ms; edge_launches += 1; cudaEventDestroy(ev2.first); cudaEventDestroy(ev2.second); }
+    edge_events.clear();
+  }
   cudaEvent_t ev[5];
   for (auto& e : ev) cudaEventCreate(&e);
   // ---------------- sort ----------------
@@ -496,6 +515,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   ENG_RC(launch_rle_write(d_idimg, w, h, d_slice_ids, ns, d_row_offsets, d_runs, stream));
   std::vector<RunRec> runs(n_runs);
   ENG_CUDA(cudaMemcpyAsync(runs.data(), d_runs, sizeof(RunRec) * n_runs, cudaMemcpyDeviceToHost, stream));
+  d2h_bytes += (double)sizeof(RunRec) * n_runs + sizeof(h_bstart) + 64;
   unsigned long long h_stats[8];
   ENG_CUDA(cudaMemcpyAsync(h_stats, mp.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
   cudaEventRecord(ev[3], stream);
@@ -608,6 +628,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   }
   std::vector<unsigned long long> pairs(n_pairs);
   if (n_pairs) ENG_CUDA(cudaMemcpy(pairs.data(), d_pairs, sizeof(unsigned long long) * n_pairs, cudaMemcpyDeviceToHost));
+  d2h_bytes += 8.0 * n_pairs + 8.0 * regions.size();
   stats[7] += 3;
   const double t_host1 = now_ms();
   for (unsigned long long key : pairs) {
@@ -829,7 +850,20 @@ int vsb200_dense_create(const vsb200_dense_opts* o, int width, int height, int u
 int vsb200_dense_push(vsb200_dense* d, const uint8_t* bgr, int row_stride_bytes, const float* flow_xy,
                       int flow_row_stride_bytes, int64_t pts, int* n_ready) {
   if (!d) return VSB200_ERR_INVALID;
-  return d->push(bgr, row_stride_bytes, flow_xy, flow_row_stride_bytes, pts, n_ready);
+  return d->push(bgr, row_stride_bytes, flow_xy, flow_row_stride_bytes, pts, n_ready, false);
+}
+
+int vsb200_dense_push_device(vsb200_dense* d, const uint8_t* dev_bgr, int row_stride_bytes, int64_t pts, int* n_ready) {
+  if (!d) return VSB200_ERR_INVALID;
+  if (d->use_flow) { set_error("push_device: flow streams use the host entry point"); return VSB200_ERR_UNSUPPORTED; }
+  return d->push(dev_bgr, row_stride_bytes, nullptr, 0, pts, n_ready, true);
+}
+
+void vsb200_dense_set_profiling(vsb200_dense* d, int time_edge_kernel) { if (d) d->time_edges = time_edge_kernel; }
+
+void vsb200_dense_io_stats(vsb200_dense* d, double out[4]) {
+  if (!d || !out) return;
+  out[0] = d->h2d_bytes; out[1] = d->d2h_bytes; out[2] = d->edge_ms; out[3] = d->edge_launches;
 }
 
 int vsb200_dense_flush(vsb200_dense* d, int* n_ready) {
@@ -874,11 +908,19 @@ void vsb200_dense_stats(vsb200_dense* d, double out[9]) {
 
 void vsb200_dense_destroy(vsb200_dense* d) { delete d; }
 
-int vsb200_dense_export_halo(vsb200_dense* d, int32_t** dev_prev, int32_t** dev_last, int32_t* max_region_id) {
-  if (!d || !dev_prev || !dev_last || !max_region_id) return VSB200_ERR_INVALID;
-  // valid right after a (non flush) chunk boundary: the id maps that seed the next chunk
-  *dev_prev = d->d_con_ids[0];
-  *dev_last = d->d_con_ids[1];
+int vsb200_dense_export_halo(vsb200_dense* d, int32_t* dev_prev_out, int32_t* dev_last_out, int32_t* max_region_id) {
+  if (!d || !dev_prev_out || !dev_last_out || !max_region_id) return VSB200_ERR_INVALID;
+  if (d->chunk_id == 0 || d->buffered != d->overlap_frames) {
+    set_error("export_halo: only valid right after a chunk boundary");
+    return VSB200_ERR_INVALID;
+  }
+  // the id maps that seed the next chunk (overlap_segmentations_, dense_segmentation.cpp:300-315)
+  if (cudaMemcpyAsync(dev_prev_out, d->d_con_ids[0], (size_t)d->n * 4, cudaMemcpyDeviceToDevice, d->stream) != cudaSuccess ||
+      cudaMemcpyAsync(dev_last_out, d->d_con_ids[1], (size_t)d->n * 4, cudaMemcpyDeviceToDevice, d->stream) != cudaSuccess ||
+      cudaStreamSynchronize(d->stream) != cudaSuccess) {
+    set_error("export_halo: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return VSB200_ERR_CUDA;
+  }
   *max_region_id = d->max_region_id;
   return VSB200_OK;
 }

@@ -35,6 +35,10 @@ constexpr unsigned long long kSerialSwitch = 256;   // grid round progress below
 constexpr int kMergeThreads = 256;
 constexpr double kFix = 4294967296.0;     // 2^32 fixed point for descriptor sums
 
+__device__ __forceinline__ void trace(const MergeParams& p, int slot, unsigned long long v) {
+  if (p.trace) { ((volatile unsigned long long*)p.trace)[slot] = v; __threadfence_system(); }
+}
+
 struct GridBar {
   cg::grid_group g;
   __device__ void sync() { g.sync(); }
@@ -268,7 +272,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
   const float edge_w = (float)b * inv_scale;
   const int mins = p.min_region_size;
   const int tid = threadIdx.x;
-  if (tid == 0) { S.wn = 0; S.cursor = 0; }
+  if (tid == 0) { S.wn = 0; S.cursor = 0; trace(p, 3, 100); }
   for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; }
   __syncthreads();
   unsigned long long rounds = 0;
@@ -369,7 +373,12 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
     if (tid == 0) S.wn = (int)(tot0 + tot1);
     __syncthreads();
     ++rounds;
+    if (tid == 0 && (rounds & 255ull) == 0) { trace(p, 4, rounds); trace(p, 5, (unsigned long long)S.wn); trace(p, 6, S.cursor); }
     if (tid == 0 && (rounds & 1023ull) == 0) atomicAdd(&p.stats[0], 1024ull);
+    if (rounds > (1ull << 24)) {        // watchdog: cannot happen (every round retires >= 1 edge)
+      if (tid == 0) { printf("vsb200 merge: serial watchdog bucket %d wn %d cursor %llu n %llu\n", b, S.wn, S.cursor, n_edges); p.stats[7] = 1ull; }
+      return true;
+    }
     // productive again? (more than a quarter of the window committed for several rounds)
     productive = (commits * 4 >= kWin) ? productive + 1 : 0;
     if (productive >= 4 && S.cursor < n_edges) {
@@ -400,7 +409,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
   // done flags of this bucket
   for (unsigned long long i = tid; i < n_edges; i += nthr) p.done[i] = 0;
   bar.sync();
+  unsigned long long guard = 0;
   while (true) {
+    if (++guard > (1ull << 22)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } break; }
     uint32_t* dst = buf ? p.live_b : p.live_a;
     const uint32_t* src = buf ? p.live_a : p.live_b;
     unsigned long long* dst_cnt = &p.counters[buf];
@@ -433,6 +444,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
     if (n_live > p.live_cap) n_live = p.live_cap;   // cannot happen: cap = largest bucket
     if (n_live == 0) break;
+    if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
     if (first_round && tid == 0) p.stats[4] = n_live;
     // ---- chain regime: let block 0 finish (or advance) the bucket in serial window mode ----
     if (!first_round && prev_live - n_live < kSerialSwitch) {
@@ -445,7 +457,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         const bool fin = serial_rounds(p, S, b, codes, n_edges);
         if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
       }
+      if (tid == 0) trace(p, 3, 2);
       bar.sync();
+      if (tid == 0) trace(p, 3, 3);
       const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
       if (finished) break;
       // productive again: next grid round re-reads this round's list (done flags filter it)
@@ -528,6 +542,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
       }
       bar.sync();
     }
+    if (tid == 0) trace(p, 3, 10);
     // ---- P3: commit (strict owners + absorption by finalised big regions); reset cluster scratch ----
     for (unsigned long long i = tid; i < n_live; i += nthr) {
       const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
@@ -581,7 +596,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     p.counters[0] = 0ull;
     p.counters[1] = 0ull;
     p.counters[2] = (unsigned long long)(epoch + 1);
-    p.counters[3] = 0ull;
+    // counters[3] (serial result) is rewritten before every barrier it is read after: never reset here
+    // (a reset could overtake blocks that have not read it yet)
   }
 }
 

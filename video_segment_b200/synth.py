@@ -41,7 +41,7 @@ class _Scene:
         self.color = rng.uniform(0.0, 255.0, size=(K_SHAPES, 3)).astype(np.float32)
         self.pos0 = np.stack([rng.uniform(0, W, K_SHAPES), rng.uniform(0, H, K_SHAPES)], 1)
         self.vel = rng.uniform(-3.0, 3.0, size=(K_SHAPES, 2))
-        self.noise_rng = np.random.default_rng([seed, 0x5EED])
+        self.seed = seed
 
     def _paint(self, img, k, t, vel_img=None):
         W, H = self.W, self.H
@@ -73,7 +73,10 @@ class _Scene:
         vel_img = np.zeros((self.H, self.W, 2), np.float32) if with_flow else None
         for k in range(K_SHAPES):
             self._paint(img, k, t, vel_img)
-        img += self.noise_rng.normal(0.0, 2.0, size=img.shape).astype(np.float32)
+        # per-frame noise stream keyed by (seed, t): frames can be generated at any offset, so every
+        # rank of a sharded run produces its own segment of the same video
+        noise_rng = np.random.default_rng([self.seed, 0x5EED, t])
+        img += noise_rng.normal(0.0, 2.0, size=img.shape).astype(np.float32)
         out = np.clip(np.rint(img), 0, 255).astype(np.uint8)
         if with_flow:
             # backward flow: where the pixel was in frame t-1 (zero on frame 0)
@@ -82,10 +85,10 @@ class _Scene:
         return np.ascontiguousarray(out)
 
 
-def synth(seed: int, W: int, H: int, T: int):
-    """Generator of T uint8 BGR frames, (H, W, 3)."""
+def synth(seed: int, W: int, H: int, T: int, start: int = 0):
+    """Generator of T uint8 BGR frames, (H, W, 3), frames start .. start + T - 1 of the video."""
     sc = _Scene(seed, W, H)
-    for t in range(T):
+    for t in range(start, start + T):
         yield sc.frame(t)
 
 

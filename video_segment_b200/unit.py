@@ -167,6 +167,30 @@ class DenseSegmentationUnit:
         self.input_frames += 1
         return self._collect(n.value)
 
+    def process_device_frame(self, dev_ptr: int, row_stride_bytes: int, pts: Optional[int] = None) -> List[dict]:
+        """Same as process_frame for a BGR24 frame already resident in device memory."""
+        n = C.c_int()
+        check(lib().vsb200_dense_push_device(self._h, C.c_void_p(dev_ptr), row_stride_bytes,
+                                             self.input_frames if pts is None else pts, C.byref(n)),
+              "vsb200_dense_push_device")
+        self.input_frames += 1
+        return self._collect(n.value)
+
+    def export_halo(self, dev_prev_ptr: int, dev_last_ptr: int) -> int:
+        """Copies the two overlap frames' region-id maps into device buffers; returns max region id."""
+        m = C.c_int32()
+        check(lib().vsb200_dense_export_halo(self._h, C.c_void_p(dev_prev_ptr), C.c_void_p(dev_last_ptr), C.byref(m)),
+              "vsb200_dense_export_halo")
+        return m.value
+
+    def set_profiling(self, time_edge_kernel: bool = True) -> None:
+        lib().vsb200_dense_set_profiling(self._h, int(time_edge_kernel))
+
+    def io_stats(self) -> dict:
+        a = (C.c_double * 4)()
+        lib().vsb200_dense_io_stats(self._h, a)
+        return dict(h2d_bytes=a[0], d2h_bytes=a[1], edge_ms=a[2], edge_launches=a[3])
+
     # --- PostProcess (segmentation_unit.cpp:154-161) ---
     def post_process(self) -> List[dict]:
         n = C.c_int()
