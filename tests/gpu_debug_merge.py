@@ -5,7 +5,7 @@ import oracle_binding as ob
 from helpers import partition_equal
 from video_segment_b200 import kernels as K
 from video_segment_b200.synth import synth_clip
-for (w,h,t) in [(96,72,6),(320,240,8),(640,480,20)]:
+for (w,h,t) in [(96,72,6),(640,480,20),(1280,720,10)]:
     c = synth_clip(12, w, h, t)
     sm = np.stack([ob.preprocess(f, threads=8) for f in c])
     minr = max(1,int(np.float32(0.01)*w*np.float32(0.01)*h*20))

@@ -160,8 +160,8 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.live_cap = max_bucket;
     mp.counters = (unsigned long long*)dalloc(16 * 8);
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
-    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc(kNumBuckets * 4 * 8) : nullptr;
-    if (mp.debug) cudaMemsetAsync(mp.debug, 0, kNumBuckets * 4 * 8, s);
+    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 16) * 8) : nullptr;
+    if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 16) * 8, s);
     mp.trace = nullptr;
     unsigned long long* h_trace = nullptr;
     std::atomic<bool> trace_stop{false};
@@ -202,7 +202,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
       break;
     }
     if (mp.debug) {
-      std::vector<unsigned long long> dbg(kNumBuckets * 4);
+      std::vector<unsigned long long> dbg(kNumBuckets * 4 + 16);
       cudaMemcpy(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost);
       FILE* f = fopen(getenv("VSB200_MERGE_DEBUG"), "w");
       if (f) {
@@ -213,6 +213,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
                   dbg[b * 4 + 1] - prev, dbg[b * 4 + 0] / 1000.0);
           prev = dbg[b * 4 + 1];
         }
+        fprintf(f, "serial phase cycles: refill %llu A %llu B12 %llu prefetch %llu B3 %llu relaxed %llu Ccompact %llu\n", dbg[kNumBuckets * 4], dbg[kNumBuckets * 4 + 1], dbg[kNumBuckets * 4 + 2], dbg[kNumBuckets * 4 + 3], dbg[kNumBuckets * 4 + 4], dbg[kNumBuckets * 4 + 5], dbg[kNumBuckets * 4 + 6]);
         fclose(f);
       }
     }

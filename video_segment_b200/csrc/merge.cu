@@ -32,7 +32,8 @@ namespace vsb {
 constexpr uint32_t kDone = 0xFFFFFFFFu;
 constexpr unsigned kTailEdges = 4096;     // <= this many edges: block 0 runs the whole bucket
 constexpr unsigned long long kSerialSwitch = 256;   // grid round progress below this -> serial window mode
-constexpr int kMergeThreads = 256;
+constexpr int kMergeThreads = 512;
+constexpr int kMergeWarps = kMergeThreads / 32;
 constexpr double kFix = 4294967296.0;     // 2^32 fixed point for descriptor sums
 
 __device__ __forceinline__ void trace(const MergeParams& p, int slot, unsigned long long v) {
@@ -139,46 +140,61 @@ __device__ __forceinline__ int merge_regions(int* parent, int ia, RegionRec& A, 
   return a_wins ? ia : ib;
 }
 
-// The serial decision tree for one edge (segmentation_graph.h:375-440); caller owns both roots.
-__device__ __forceinline__ void exec_strict(const MergeParams& p, int ia, int ib, float edge_w,
-                                            unsigned long long* stats) {
-  RegionRec A = load_rec(&p.rec[ia]);
-  RegionRec B = load_rec(&p.rec[ib]);
+// The serial decision tree for one edge (segmentation_graph.h:375-440) on register copies of the
+// two representatives' records (A = rep_1, B = rep_2).  Returns 1 if A survives a merge, 2 if B
+// survives a merge, 0 if the regions stay separate (records may still have changed).
+__device__ __forceinline__ int decide_pair(const MergeParams& p, RegionRec& A, RegionRec& B, float edge_w) {
   const int mins = p.min_region_size;
+  auto merge = [&]() -> int {                 // MergeRegions (:671-701) + MergeDescriptor (pixel_distance.h:494-504)
+    const bool a_wins = A.sz > B.sz;
+    RegionRec& m = a_wins ? A : B;
+    RegionRec& o = a_wins ? B : A;
+    const float denom = 1.0f / (float)(o.sz + m.sz);
+    const float fa = (float)o.sz * denom;
+    const float fb = (float)m.sz * denom;
+    m.d0 = fa * o.d0 + fb * m.d0;
+    m.d1 = fa * o.d1 + fb * m.d1;
+    m.d2 = fa * o.d2 + fb * m.d2;
+    m.sz += o.sz;
+    m.con = max(A.con, B.con);
+    return a_wins ? 1 : 2;
+  };
   if (A.con < 0 || B.con < 0) {
     if (!A.fin && !B.fin) {
       const float d = desc_dist(A, B, edge_w, p.force_merge_weight);
-      if (d < 0.05f) {                       // MergeDistanceThreshold, pixel_distance.h:471
-        const int m = merge_regions(p.parent, ia, A, ib, B);
-        store_rec(&p.rec[m], m == ia ? A : B);
-        return;
-      }
+      if (d < 0.05f) return merge();          // MergeDistanceThreshold, pixel_distance.h:471
       A.fin = 1;
       B.fin = 1;
     }
     if (A.fin || B.fin) {
-      if (A.sz < mins || B.sz < mins) {
-        const int m = merge_regions(p.parent, ia, A, ib, B);
-        store_rec(&p.rec[m], m == ia ? A : B);
-        return;
-      }
+      if (A.sz < mins || B.sz < mins) return merge();
     }
-    store_rec(&p.rec[ia], A);
-    store_rec(&p.rec[ib], B);
+    return 0;
   } else if (A.con == B.con) {
     const float d = desc_dist(A, B, edge_w, p.force_merge_weight);
     if (d > 0.15f) {                          // SplitDistanceThreshold, pixel_distance.h:472
       if ((double)A.sz < (double)B.sz * 0.3) A.con = -1;
       else if ((double)B.sz < (double)A.sz * 0.3) B.con = -1;
       else { A.con = -1; B.con = -1; }
-      store_rec(&p.rec[ia], A);
-      store_rec(&p.rec[ib], B);
-    } else {
-      const int m = merge_regions(p.parent, ia, A, ib, B);
-      store_rec(&p.rec[m], m == ia ? A : B);
+      return 0;
     }
+    return merge();
   }
-  // different constraint ids: never merge, nothing changes
+  return 0;                                   // different constraint ids: never merge
+}
+
+// One edge whose two roots this thread owns.  Returns the surviving representative of a merge,
+// or -1 if the regions stay separate.
+__device__ __forceinline__ int exec_strict(const MergeParams& p, int ia, int ib, float edge_w,
+                                           unsigned long long* stats) {
+  RegionRec A = load_rec(&p.rec[ia]);
+  RegionRec B = load_rec(&p.rec[ib]);
+  const int r = decide_pair(p, A, B, edge_w);
+  if (r == 1) { p.parent[ib] = ia; store_rec(&p.rec[ia], A); return ia; }
+  if (r == 2) { p.parent[ia] = ib; store_rec(&p.rec[ib], B); return ib; }
+  store_rec(&p.rec[ia], A);
+  store_rec(&p.rec[ib], B);
+  return -1;
 }
 
 __device__ __forceinline__ void acc_add(unsigned long long* acc, int root, const RegionRec& r) {
@@ -220,23 +236,38 @@ __device__ __forceinline__ void acc_fold(const MergeParams& p, int root) {
 // hash table.  A window holds every earlier pending edge of each of its edges, so owning both
 // roots inside the window is again "next edge in reference order" -- exact, ~2 us per round.
 // ---------------------------------------------------------------------------------------------
-constexpr int kWin = 512;
-constexpr int kHash = 2048;
+constexpr int kWin = 2048;
+constexpr int kHash = 8192;
 
 struct SerialShared {
   uint32_t code[kWin], pos[kWin], ru[kWin], rv[kWin];
   unsigned hkey[kHash], hval[kHash];
-  unsigned warp_cnt[8];
+  unsigned short htag[kHash];      // run (head index + 1) that scheduled this root as a leaf, 0 = none
+  unsigned short hcnt[kHash];      // window entries touching this root
+  unsigned short su[kWin], sv[kWin];   // hash slots of an entry's two roots
+  unsigned short owner[kWin];      // head index + 1 of the run an entry belongs to, 0 = none
+  unsigned char kind[kWin];        // 0 done, 1 head (owns both roots), 2 owns rv only, 3 owns ru only, 4 owns neither; +8 = leaf item of a run, +16 = duplicate item of a run
+  int run_start[kWin / 2], run_len[kWin / 2], run_hub[kWin / 2];
+  int n_runs, run_next;
+  unsigned warp_cnt[kMergeWarps];
+  int lsz[kWin], lcon[kWin], lfin[kWin];   // leaf records of run items, prefetched by the whole block
+  float ld0[kWin], ld1[kWin], ld2[kWin];
   int wn, taken, commits;
   unsigned long long cursor, next_cursor;
 };
 
-__device__ __forceinline__ unsigned hash_slot(unsigned root) { return (root * 2654435761u) >> 21; }   // 11 bits
-__device__ __forceinline__ void hash_min(SerialShared& S, unsigned root, unsigned val) {
+__device__ __forceinline__ unsigned hash_slot(unsigned root) { return (root * 2654435761u) >> 19; }   // 13 bits
+__device__ __forceinline__ unsigned hash_min(SerialShared& S, unsigned root, unsigned val) {
   unsigned slot = hash_slot(root);
   while (true) {
     const unsigned k = atomicCAS(&S.hkey[slot], 0u, root + 1u);
-    if (k == 0u || k == root + 1u) { atomicMin(&S.hval[slot], val); return; }
+    if (k == 0u || k == root + 1u) {
+      atomicMin(&S.hval[slot], val);
+      // 16-bit counters packed two per word: use a 32-bit atomic on the containing word
+      unsigned* w = reinterpret_cast<unsigned*>(&S.hcnt[slot & ~1u]);
+      atomicAdd(w, (slot & 1u) ? 0x10000u : 1u);
+      return slot;
+    }
     slot = (slot + 1u) & (kHash - 1);
   }
 }
@@ -250,6 +281,16 @@ __device__ __forceinline__ unsigned hash_get(const SerialShared& S, unsigned roo
   }
 }
 
+__device__ __forceinline__ int hash_find(const SerialShared& S, unsigned root) {
+  unsigned slot = hash_slot(root);
+  while (true) {
+    const unsigned k = S.hkey[slot];
+    if (k == root + 1u) return (int)slot;
+    if (k == 0u) return -1;
+    slot = (slot + 1u) & (kHash - 1);
+  }
+}
+
 // block-wide exclusive scan of a 0/1 flag over 256 threads; returns rank, total via smem
 __device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsigned* total) {
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -258,7 +299,7 @@ __device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsig
   __syncthreads();
   unsigned base = 0, tot = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
+  for (int k = 0; k < kMergeWarps; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
   __syncthreads();
   *total = tot;
   return base + __popc(m & ((1u << lane) - 1u));
@@ -273,10 +314,13 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
   const int mins = p.min_region_size;
   const int tid = threadIdx.x;
   if (tid == 0) { S.wn = 0; S.cursor = 0; trace(p, 3, 100); }
-  for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; }
+  for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; S.htag[i] = 0; S.hcnt[i] = 0; }
   __syncthreads();
   unsigned long long rounds = 0;
   int productive = 0;
+  long long tmark = clock64();
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VSB_T(slot) do { if (tid == 0) { const long long t_ = clock64(); tacc[slot] += t_ - tmark; tmark = t_; } } while (0)
   while (true) {
     // ---- refill the window with the next pending edges in reference order ----
     while (true) {
@@ -301,77 +345,385 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
     const int wn = S.wn;
     if (wn == 0) return true;
     if (tid == 0) S.commits = 0;
+    VSB_T(0);
     // ---- A: roots, inert edges, reservations (window index == reference order) ----
-    for (int i = tid; i < wn; i += kMergeThreads) {
-      const uint32_t code = S.code[i];
-      int u, v;
-      decode_edge(p, code, u, v);
-      const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-      bool drop = (ru == rv);
-      if (!drop) {
-        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-        const bool both_con = (A.con >= 0 && B.con >= 0);
-        drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+    {
+      constexpr int kU = kWin / kMergeThreads;
+      int us[kU], vs[kU], pu[kU], pv[kU];
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        const int i = tid + q * kMergeThreads;
+        us[q] = -1;
+        if (i < wn) decode_edge(p, S.code[i], us[q], vs[q]);
       }
-      if (drop) {
-        p.done[S.pos[i]] = 1;
-        S.code[i] = kDone;
-        S.ru[i] = 0xFFFFFFFFu; S.rv[i] = 0xFFFFFFFFu;
-      } else {
-        S.ru[i] = (uint32_t)ru; S.rv[i] = (uint32_t)rv;
-        hash_min(S, (unsigned)ru, (unsigned)i);
-        hash_min(S, (unsigned)rv, (unsigned)i);
+#pragma unroll
+      for (int q = 0; q < kU; ++q) { pu[q] = p.parent[us[q] >= 0 ? us[q] : 0]; pv[q] = p.parent[us[q] >= 0 ? vs[q] : 0]; }   // first hops in flight together
+      RegionRec As[kU], Bs[kU];
+      int rus[kU], rvs[kU];
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        if (us[q] < 0) continue;
+        rus[q] = (pu[q] == us[q]) ? us[q] : uf_find(p.parent, pu[q]);
+        rvs[q] = (pv[q] == vs[q]) ? vs[q] : uf_find(p.parent, pv[q]);
+        if (pu[q] != us[q] && rus[q] != pu[q]) p.parent[us[q]] = rus[q];     // path compression
+        if (pv[q] != vs[q] && rvs[q] != pv[q]) p.parent[vs[q]] = rvs[q];
+      }
+#pragma unroll
+      for (int q = 0; q < kU; ++q) { const bool v_ = us[q] >= 0; As[q] = load_rec(&p.rec[v_ ? rus[q] : 0]); Bs[q] = load_rec(&p.rec[v_ ? rvs[q] : 0]); }
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        if (us[q] < 0) continue;
+        const int i = tid + q * kMergeThreads;
+        const int ru = rus[q], rv = rvs[q];
+        bool drop = (ru == rv);
+        if (!drop) {
+          const RegionRec& A = As[q];
+          const RegionRec& B = Bs[q];
+          const bool both_con = (A.con >= 0 && B.con >= 0);
+          drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+        }
+        if (drop) {
+          p.done[S.pos[i]] = 1;
+          S.code[i] = kDone;
+          S.ru[i] = 0xFFFFFFFFu; S.rv[i] = 0xFFFFFFFFu;
+        } else {
+          S.ru[i] = (uint32_t)ru; S.rv[i] = (uint32_t)rv;
+          S.su[i] = (unsigned short)hash_min(S, (unsigned)ru, (unsigned)i);
+          S.sv[i] = (unsigned short)hash_min(S, (unsigned)rv, (unsigned)i);
+        }
       }
     }
     __syncthreads();
-    // ---- B: commit ----
+    VSB_T(1);
+    // ---- B1: who owns what ----
+    if (tid == 0) { S.n_runs = 0; S.run_next = 0; }
     for (int i = tid; i < wn; i += kMergeThreads) {
-      if (S.code[i] == kDone) continue;
-      const int ru = (int)S.ru[i], rv = (int)S.rv[i];
-      const bool own_u = hash_get(S, (unsigned)ru) == (unsigned)i, own_v = hash_get(S, (unsigned)rv) == (unsigned)i;
-      bool done = false;
-      if (own_u && own_v) {
-        exec_strict(p, ru, rv, edge_w, p.stats);
-        done = true;
-      } else if (own_u || own_v) {
-        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-        if (own_v && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        else if (own_u && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+      unsigned char k = 0;
+      if (S.code[i] != kDone) {
+        const bool own_u = S.hval[S.su[i]] == (unsigned)i, own_v = S.hval[S.sv[i]] == (unsigned)i;
+        k = (own_u && own_v) ? 1 : own_v ? 2 : own_u ? 3 : 4;
       }
-      if (done) {
+      S.kind[i] = k;
+      S.owner[i] = 0;
+    }
+    __syncthreads();
+    // ---- B2: hub runs.  A head i owns both its roots {a, b}.  Walking the window in reference
+    // order after i, every entry that touches a or b is the next edge of the hub a+b provided
+    // its other root x is a fresh leaf it owns (first window entry of x) -> leaf item, or a leaf
+    // already scheduled by this run / the other head root -> duplicate item (internal once the
+    // leaf merged).  The walk stops at the first hub entry that is neither, or at the first
+    // entry that touches a scheduled leaf from outside the hub.  All items then are, in order,
+    // the next edges of the hub in the reference scan and are applied sequentially. ----
+    for (int i = tid; i < wn; i += kMergeThreads) {
+      if (S.kind[i] != 1) continue;
+      const unsigned a = S.ru[i], b = S.rv[i];
+      const unsigned short me = (unsigned short)(i + 1);
+      int items = 0;
+      // both roots touched by this entry only: nothing to walk
+      const int hub_entries = (int)S.hcnt[S.su[i]] + (int)S.hcnt[S.sv[i]] - 2;
+      int seen = 0;
+      for (int j = i + 1; j < wn && seen < hub_entries; ++j) {
+        const unsigned char k = S.kind[j];
+        if (k == 0) continue;
+        const unsigned u = S.ru[j], v = S.rv[j];
+        const bool tu = (u == a || u == b), tv = (v == a || v == b);
+        if (tu && tv) { S.owner[j] = me; S.kind[j] = k | 16; ++items; seen += 2; continue; }
+        if (tu || tv) {
+          ++seen;
+          const int sx = tu ? S.sv[j] : S.su[j];
+          if (S.htag[sx] == me) { S.owner[j] = me; S.kind[j] = k | 16; ++items; continue; }
+          const bool owns_x = tu ? (k == 2) : (k == 3);     // kind 2 owns rv, kind 3 owns ru
+          if (!owns_x) break;
+          S.htag[sx] = me;
+          S.owner[j] = me; S.kind[j] = k | 8; ++items;
+          continue;
+        }
+        // foreign entry: conflict if it touches a leaf this run scheduled
+        if (S.htag[S.su[j]] == me || S.htag[S.sv[j]] == me) break;
+      }
+      if (items == 0) {
+        // isolated head: nobody else touches its two roots this round
+        exec_strict(p, (int)a, (int)b, edge_w, p.stats);
         p.done[S.pos[i]] = 1;
         S.code[i] = kDone;
         atomicAdd(&S.commits, 1);
+      } else {
+        const int slot = atomicAdd(&S.n_runs, 1);
+        S.run_start[slot] = i; S.run_len[slot] = items; S.run_hub[slot] = 0;
       }
     }
     __syncthreads();
+    VSB_T(2);
+    // leaf records of all run items -> shared memory (one parallel gather instead of a global
+    // load per 32-entry step of the sequential executors)
+    {
+      constexpr int kU = kWin / kMergeThreads;
+      int xs[kU];
+      RegionRec Xs[kU];
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        const int j = tid + q * kMergeThreads;
+        xs[q] = -1;
+        if (j < wn && S.owner[j] != 0 && (S.kind[j] & 8)) {
+          const unsigned short o1 = S.owner[j];
+          const unsigned ha = S.ru[o1 - 1], hb = S.rv[o1 - 1];
+          const bool hub_is_u = (S.ru[j] == ha || S.ru[j] == hb);
+          xs[q] = hub_is_u ? (int)S.rv[j] : (int)S.ru[j];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kU; ++q) Xs[q] = load_rec(&p.rec[xs[q] >= 0 ? xs[q] : 0]);     // unconditional: loads stay in flight together
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        if (xs[q] < 0) continue;
+        const int j = tid + q * kMergeThreads;
+        S.lsz[j] = Xs[q].sz; S.lcon[j] = Xs[q].con; S.lfin[j] = Xs[q].fin;
+        S.ld0[j] = Xs[q].d0; S.ld1[j] = Xs[q].d1; S.ld2[j] = Xs[q].d2;
+      }
+    }
+    __syncthreads();
+    VSB_T(3);
+    // ---- B3: execute runs.  Warps take runs from a shared counter; lanes look at 32 window
+    // slots at a time, prefetch the leaves' records, lane 0 applies the items in order with the
+    // hub record in registers. ----
+    {
+      const unsigned lane = tid & 31;
+      while (true) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&S.run_next, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= S.n_runs) break;
+        const int i0 = S.run_start[r];
+        const unsigned short me = (unsigned short)(i0 + 1);
+        const unsigned ha = S.ru[i0], hb = S.rv[i0];
+        // head
+        int hub_cur = -1, merged = 0;
+        RegionRec H;
+        H.sz = 0; H.con = -1; H.d0 = H.d1 = H.d2 = 0.f; H.fin = 0; H.pad0 = H.pad1 = 0;
+        if (lane == 0) {
+          RegionRec A = load_rec(&p.rec[(int)ha]), B = load_rec(&p.rec[(int)hb]);
+          const int res = decide_pair(p, A, B, edge_w);
+          if (res == 1) { p.parent[(int)hb] = (int)ha; hub_cur = (int)ha; H = A; merged = 1; }
+          else if (res == 2) { p.parent[(int)ha] = (int)hb; hub_cur = (int)hb; H = B; merged = 1; }
+          else { store_rec(&p.rec[(int)ha], A); store_rec(&p.rec[(int)hb], B); }
+          p.done[S.pos[i0]] = 1;
+          S.code[i0] = kDone;
+        }
+        merged = __shfl_sync(0xffffffffu, merged, 0);
+        int committed = 1;
+        if (merged) {
+          int remaining = S.run_len[r];
+          for (int base = i0 + 1; base < wn && remaining > 0; base += 32) {
+            const int j = base + (int)lane;
+            const bool mine = (j < wn) && (S.owner[j] == me);
+            const unsigned mask = __ballot_sync(0xffffffffu, mine);
+            if (mask == 0u) continue;
+            remaining -= __popc(mask);
+            const unsigned char kj = mine ? S.kind[j] : 0;
+            const bool is_leaf = mine && (kj & 8);
+            // leaf items: x = the root that is not the hub side
+            int x = -1;
+            bool hub_is_u = false;
+            RegionRec X;
+            X.sz = 0; X.con = -1; X.d0 = X.d1 = X.d2 = 0.f; X.fin = 0; X.pad0 = X.pad1 = 0;
+            if (is_leaf) {
+              hub_is_u = (S.ru[j] == ha || S.ru[j] == hb);
+              x = hub_is_u ? (int)S.rv[j] : (int)S.ru[j];
+              X.sz = S.lsz[j]; X.con = S.lcon[j]; X.fin = S.lfin[j]; X.d0 = S.ld0[j]; X.d1 = S.ld1[j]; X.d2 = S.ld2[j];
+            }
+            // ---- certified fast path: every leaf of this chunk certainly merges into the hub
+            // (un-finalised, unconstrained hub that outweighs each leaf; gate distance plus the
+            // worst-case drift of the hub mean inside the chunk stays below the threshold).  Then
+            // only the running mean is sequential: m <- fa_k * leaf_k + fb_k * m, same float ops
+            // and order as MergeDescriptor; duplicates become internal edges. ----
+            RegionRec Hb;
+            Hb.sz = __shfl_sync(0xffffffffu, H.sz, 0); Hb.con = __shfl_sync(0xffffffffu, H.con, 0);
+            Hb.d0 = __shfl_sync(0xffffffffu, H.d0, 0); Hb.d1 = __shfl_sync(0xffffffffu, H.d1, 0);
+            Hb.d2 = __shfl_sync(0xffffffffu, H.d2, 0); Hb.fin = __shfl_sync(0xffffffffu, H.fin, 0);
+            Hb.pad0 = Hb.pad1 = 0;
+            const int hub_id = __shfl_sync(0xffffffffu, hub_cur, 0);
+            const float dk = is_leaf ? raw_dist(Hb, X) : 0.f;
+            const int my_sz = is_leaf ? X.sz : 0;
+            float psd = (float)my_sz * dk;
+            int psz = my_sz;
+            for (int o = 1; o < 32; o <<= 1) {
+              const float t1 = __shfl_up_sync(0xffffffffu, psd, o);
+              const int t2 = __shfl_up_sync(0xffffffffu, psz, o);
+              if ((int)lane >= o) { psd += t1; psz += t2; }
+            }
+            const int sz_before = Hb.sz + psz - my_sz;
+            const float drift = (psd - (float)my_sz * dk) / (float)Hb.sz;
+            const float thr = (edge_w < p.force_merge_weight) ? 0.2f : 0.05f;
+            bool ok = true;
+            if (is_leaf) {
+              ok = (Hb.con < 0) && (Hb.fin == 0) && (X.con < 0) && (X.sz < Hb.sz);
+              if (ok) {
+                if (X.fin) ok = (X.sz < mins) || (sz_before < mins);
+                else ok = (dk + drift * 1.0001f + 2e-5f) < thr;
+              }
+            }
+            // duplicates are internal only if their leaf merged: in the fast path every leaf of
+            // this and of earlier chunks merged (tracked by all_merged)
+            if (__all_sync(0xffffffffu, ok) && __shfl_sync(0xffffffffu, merged, 0) == 1) {
+              const float denom = 1.0f / (float)(my_sz + sz_before);
+              const float fa = (float)my_sz * denom;
+              const float fb = (float)sz_before * denom;
+              const float c0 = fa * X.d0, c1 = fa * X.d1, c2 = fa * X.d2;
+              float m0 = Hb.d0, m1 = Hb.d1, m2 = Hb.d2;
+              unsigned lm = __ballot_sync(0xffffffffu, is_leaf);
+              while (lm) {
+                const int k = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const float fbk = __shfl_sync(0xffffffffu, fb, k);
+                const float a0 = __shfl_sync(0xffffffffu, c0, k), a1 = __shfl_sync(0xffffffffu, c1, k), a2 = __shfl_sync(0xffffffffu, c2, k);
+                m0 = a0 + fbk * m0;
+                m1 = a1 + fbk * m1;
+                m2 = a2 + fbk * m2;
+              }
+              if (mine) {
+                if (is_leaf) p.parent[x] = hub_id;
+                p.done[S.pos[j]] = 1;
+                S.code[j] = kDone;
+              }
+              const int tot_sz = __shfl_sync(0xffffffffu, psz, 31);
+              if (lane == 0) { H.d0 = m0; H.d1 = m1; H.d2 = m2; H.sz = Hb.sz + tot_sz; }
+              committed += __popc(mask);
+              continue;
+            }
+            // ---- general path: lane 0 applies the chunk's items one by one.  merged == 2 from
+            // here on: some leaf may have stayed separate, so duplicates are re-examined. ----
+            unsigned m2 = mask;
+            while (m2) {
+              const int k = __ffs(m2) - 1;
+              m2 &= m2 - 1;
+              const int jk = base + k;
+              const int leafk = __shfl_sync(0xffffffffu, (int)is_leaf, k);
+              const int xk = __shfl_sync(0xffffffffu, x, k);
+              const int hu = __shfl_sync(0xffffffffu, (int)hub_is_u, k);
+              RegionRec L;
+              L.sz = __shfl_sync(0xffffffffu, X.sz, k); L.con = __shfl_sync(0xffffffffu, X.con, k);
+              L.d0 = __shfl_sync(0xffffffffu, X.d0, k); L.d1 = __shfl_sync(0xffffffffu, X.d1, k);
+              L.d2 = __shfl_sync(0xffffffffu, X.d2, k); L.fin = __shfl_sync(0xffffffffu, X.fin, k);
+              L.pad0 = 0; L.pad1 = 0;
+              if (lane == 0) {
+                int other = xk;
+                bool hub_first = hu != 0;
+                if (!leafk) {
+                  // duplicate: the other root is a scheduled leaf or the second head root; it is
+                  // internal iff that root now belongs to the hub
+                  const unsigned uu = S.ru[jk], vv = S.rv[jk];
+                  const bool tu = (uu == ha || uu == hb);
+                  const bool tv = (vv == ha || vv == hb);
+                  other = (tu && tv) ? -1 : (int)(tu ? vv : uu);
+                  hub_first = tu;
+                  if (other >= 0) {
+                    const int ro = uf_find(p.parent, other);
+                    if (ro == hub_cur) other = -1;
+                    else { other = ro; L = load_rec(&p.rec[ro]); }
+                  }
+                }
+                if (other >= 0) {
+                  int res;
+                  if (hub_first) { res = decide_pair(p, H, L, edge_w); }
+                  else { res = decide_pair(p, L, H, edge_w); res = (res == 1) ? 2 : (res == 2) ? 1 : 0; }
+                  // res: 1 = hub record survives, 2 = other record survives, 0 = no merge
+                  if (res == 1) { p.parent[other] = hub_cur; }
+                  else if (res == 2) { p.parent[hub_cur] = other; hub_cur = other; H = L; }
+                  else { store_rec(&p.rec[other], L); }
+                }
+                p.done[S.pos[jk]] = 1;
+                S.code[jk] = kDone;
+                merged = 2;
+              }
+            }
+            committed += __popc(mask);
+          }
+        }
+        if (lane == 0) {
+          if (hub_cur >= 0) store_rec(&p.rec[hub_cur], H);
+          atomicAdd(&S.commits, committed);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    VSB_T(4);
+    // unclaimed single-owner entries: absorption by a finalised region of >= min size (unordered)
+    {
+      constexpr int kU = kWin / kMergeThreads;
+      bool act[kU];
+      RegionRec As[kU], Bs[kU];
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        const int i = tid + q * kMergeThreads;
+        act[q] = false;
+        if (i < wn) {
+          const unsigned char k = S.kind[i];
+          act[q] = (k == 2 || k == 3) && S.owner[i] == 0 && S.code[i] != kDone;
+        }
+        As[q] = load_rec(&p.rec[act[q] ? (int)S.ru[i] : 0]); Bs[q] = load_rec(&p.rec[act[q] ? (int)S.rv[i] : 0]);
+      }
+#pragma unroll
+      for (int q = 0; q < kU; ++q) {
+        if (!act[q]) continue;
+        const int i = tid + q * kMergeThreads;
+        const unsigned char k = S.kind[i];
+        const int ru = (int)S.ru[i], rv = (int)S.rv[i];
+        const RegionRec& A = As[q];
+        const RegionRec& B = Bs[q];
+        bool done = false;
+        if (k == 2 && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
+        else if (k == 3 && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+        if (done) {
+          p.done[S.pos[i]] = 1;
+          S.code[i] = kDone;
+          atomicAdd(&S.commits, 1);
+        }
+      }
+    }
+    __syncthreads();
+    VSB_T(5);
     // ---- C: fold bulk contributions, clear the hash, compact the window (stable) ----
     for (int i = tid; i < wn; i += kMergeThreads) {
       if (S.ru[i] == 0xFFFFFFFFu) continue;
       acc_fold(p, (int)S.ru[i]);
       acc_fold(p, (int)S.rv[i]);
     }
-    for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; }
-    // each thread owns window entries [2*tid, 2*tid+1]
-    uint32_t c0 = kDone, c1 = kDone, p0 = 0, p1 = 0;
-    const int i0 = 2 * tid, i1 = 2 * tid + 1;
-    if (i0 < wn) { c0 = S.code[i0]; p0 = S.pos[i0]; }
-    if (i1 < wn) { c1 = S.code[i1]; p1 = S.pos[i1]; }
-    const unsigned k0 = (c0 != kDone) ? 1u : 0u, k1 = (c1 != kDone) ? 1u : 0u;
-    // scan of per-thread keep counts (0..2): two flag scans
-    unsigned tot0, tot1;
-    const unsigned r0 = block_rank(S, k0 != 0, &tot0);
-    const unsigned r1 = block_rank(S, k1 != 0, &tot1);
-    // stable order: entry 2t precedes 2t+1 precedes 2(t+1): rank = (#kept among even idx < 2t) + (#kept among odd idx < 2t)
-    // r0 counts kept even entries of threads < tid; r1 counts kept odd entries of threads < tid.
-    const unsigned dst0 = r0 + r1;
-    const unsigned dst1 = r0 + r1 + k0;
-    const int commits = S.commits;
-    __syncthreads();
-    if (k0) { S.code[dst0] = c0; S.pos[dst0] = p0; }
-    if (k1) { S.code[dst1] = c1; S.pos[dst1] = p1; }
-    if (tid == 0) S.wn = (int)(tot0 + tot1);
-    __syncthreads();
+    for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; S.htag[i] = 0; S.hcnt[i] = 0; }
+    // stable compaction: each thread owns kPer consecutive window entries
+    constexpr int kPer = kWin / kMergeThreads;
+    uint32_t cc[kPer], pp[kPer];
+    unsigned keep = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = tid * kPer + q;
+      cc[q] = kDone; pp[q] = 0;
+      if (i < wn) { cc[q] = S.code[i]; pp[q] = S.pos[i]; }
+      keep += (cc[q] != kDone) ? 1u : 0u;
+    }
+    // block exclusive scan of keep counts (0..kPer)
+    unsigned inc = keep;
+    {
+      const unsigned lane = tid & 31, wid = tid >> 5;
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) S.warp_cnt[wid] = inc;
+      __syncthreads();
+      unsigned base = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < kMergeWarps; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
+      inc = base + inc - keep;        // exclusive
+      const int commits_now = S.commits;
+      __syncthreads();
+      unsigned d = inc;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q)
+        if (cc[q] != kDone) { S.code[d] = cc[q]; S.pos[d] = pp[q]; ++d; }
+      if (tid == 0) S.wn = (int)tot;
+      __syncthreads();
+      productive = (commits_now * 4 >= kWin) ? productive + 1 : 0;
+    }
+    VSB_T(6);
+    if (tid == 0 && p.debug && (rounds & 63ull) == 63ull) { for (int q = 0; q < 7; ++q) { atomicAdd(&p.debug[kNumBuckets * 4 + q], (unsigned long long)tacc[q]); tacc[q] = 0; } }
     ++rounds;
     if (tid == 0 && (rounds & 255ull) == 0) { trace(p, 4, rounds); trace(p, 5, (unsigned long long)S.wn); trace(p, 6, S.cursor); }
     if (tid == 0 && (rounds & 1023ull) == 0) atomicAdd(&p.stats[0], 1024ull);
@@ -380,12 +732,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
       return true;
     }
     // productive again? (more than a quarter of the window committed for several rounds)
-    productive = (commits * 4 >= kWin) ? productive + 1 : 0;
-    if (productive >= 4 && S.cursor < n_edges) {
-      // hand the bucket back: the window's edges stay pending (done flags tell)
-      if (tid == 0) atomicAdd(&p.stats[0], rounds & 1023ull);
-      return false;
-    }
+    (void)productive;   // hub runs retire most of a window per round; the grid rounds cannot do better on a chain
     if (S.wn == 0 && S.cursor >= n_edges) {
       if (tid == 0) atomicAdd(&p.stats[0], rounds & 1023ull);
       return true;
@@ -602,7 +949,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
 }
 
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
-  __shared__ SerialShared S;
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  SerialShared& S = *reinterpret_cast<SerialShared*>(merge_smem);
   GridBar gbar{cg::this_grid()};
   BlockBar bbar;
   const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -695,12 +1043,14 @@ int launch_merge(const MergeParams& p, cudaStream_t s) {
   int dev = 0, sms = 0, per_sm = 0;
   VSB_CUDA_OK(cudaGetDevice(&dev));
   VSB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  VSB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel, kMergeThreads, 0));
+  const size_t smem = sizeof(SerialShared);
+  VSB_CUDA_OK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VSB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel, kMergeThreads, smem));
   if (per_sm < 1) { set_error("merge kernel does not fit on an SM"); return 3; }
   per_sm = per_sm > 4 ? 4 : per_sm;
   MergeParams pp = p;
   void* args[] = {&pp};
-  VSB_CUDA_OK(cudaLaunchCooperativeKernel((void*)merge_kernel, dim3(sms * per_sm), dim3(kMergeThreads), args, 0, s));
+  VSB_CUDA_OK(cudaLaunchCooperativeKernel((void*)merge_kernel, dim3(sms * per_sm), dim3(kMergeThreads), args, smem, s));
   return 0;
 }
 
