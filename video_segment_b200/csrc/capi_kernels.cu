@@ -152,7 +152,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.res = (unsigned long long*)dalloc(nodes * 8);
     mp.acc = (unsigned long long*)dalloc(nodes * 32);
     mp.cl = (int*)dalloc(nodes * 4);
-    mp.hull = (int*)dalloc(nodes * 32);
+    mp.hull = (NodeScratch*)dalloc(nodes * sizeof(NodeScratch));
     mp.live_a = (uint32_t*)dalloc(max_bucket * 16);
     mp.live_b = (uint32_t*)dalloc(max_bucket * 16);
     mp.live_aux = (uint32_t*)dalloc(max_bucket * 4);

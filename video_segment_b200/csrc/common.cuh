@@ -63,6 +63,23 @@ struct __align__(32) RegionRec {
   int pad0, pad1;
 };
 
+// Per-node scratch of the window certification stage (merge.cu).  A small root uses its slot as the
+// record of the sub-cluster it represents, a big root ("hub") as its absorption bound.  Idle state
+// between windows: mn = 0x7f7f7f7f, mx = 0, flags = 0, con = kNoCon, mass = 0, hubs = -1, rbits = 0, num = 0.
+struct __align__(16) NodeScratch {
+  int mn[3];                 // colour hull of the members (float bits; colours are >= 0)
+  int mx[3];
+  int flags;                 // kSc* bits
+  int con;                   // single constraint id met so far (kNoCon = none)
+  int mass;                  // voxels of the members / of the atoms a hub may absorb
+  int hub0, hub1;            // big roots adjacent to the sub-cluster (-1 = none)
+  int rbits;                 // hub: max distance to an absorbable atom (float bits)
+  unsigned long long num;    // spare
+  int claim;                 // window tag of the last once-per-atom claim (never reset)
+  int frozen;                // window tag in which this hub's decision-relevant state is certified constant
+};
+constexpr int kNoCon = 0x7f7f7f7f;
+
 struct MergeParams {
   int w, h, slots;                 // graph geometry; nodes = slots * w * h
   int min_region_size;
@@ -76,7 +93,7 @@ struct MergeParams {
   unsigned long long* res;         // [nodes] epoch-tagged reservations
   unsigned long long* acc;         // [nodes][4] fixed-point accumulators: sz, d0, d1, d2
   int* cl;                         // [nodes] scratch cluster union-find
-  int* hull;                       // [nodes][8]: min0..2, max0..2, flags, conmin (float bits as int)
+  NodeScratch* hull;               // [nodes] certification scratch of the current window (idle between windows)
   unsigned char* done;             // [max bucket edges] per-position done flags of the current bucket
   uint32_t* live_aux;              // [live_cap] cluster root of a live entry (first round of a bucket)
   uint32_t* live_a;                // live edge buffers: (code, ru, rv, position)
@@ -87,7 +104,6 @@ struct MergeParams {
   unsigned long long* trace;       // optional mapped host memory: live progress markers (debugging hangs)
   unsigned long long* debug;       // optional [2048][4]: ns, cumulative rounds, edges, pending after pruning
 };
-size_t merge_scratch_bytes(int w, int h, int slots, unsigned long long max_bucket_edges);
 int launch_merge(const MergeParams& p, cudaStream_t s);
 int launch_init_nodes(const float* frame, const int* constraint_ids, int slot, int w, int h, int* parent,
                       RegionRec* rec, cudaStream_t s);

@@ -159,7 +159,7 @@ int vsb200_dense::init() {
   ENG_CUDA(cudaMalloc(&mp.res, nodes * 8));
   ENG_CUDA(cudaMalloc(&mp.acc, nodes * 32));
   ENG_CUDA(cudaMalloc(&mp.cl, nodes * 4));
-  ENG_CUDA(cudaMalloc(&mp.hull, nodes * 32));
+  ENG_CUDA(cudaMalloc(&mp.hull, nodes * sizeof(NodeScratch)));
   ENG_CUDA(cudaMalloc(&mp.counters, 16 * 8));
   mp.stats = mp.counters + 8;
   mp.debug = nullptr;

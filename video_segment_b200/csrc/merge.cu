@@ -77,6 +77,17 @@ __device__ __forceinline__ int cl_find(const int* cl, int x) {
   while (p != x) { x = p; p = cl[x]; }
   return x;
 }
+// find with path halving; only used once all unions of the window are done (plain stores towards the root are benign)
+__device__ __forceinline__ int cl_find_compress(int* cl, int x) {
+  int p = cl[x];
+  while (p != x) {
+    const int gp = cl[p];
+    if (gp != p) cl[x] = gp;
+    x = p;
+    p = gp;
+  }
+  return x;
+}
 __device__ __forceinline__ void cl_union(int* cl, int a, int b) {
   while (true) {
     a = cl_find(cl, a);
@@ -308,7 +319,7 @@ __device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsig
 // Returns true when the bucket is finished, false when the window became productive again
 // (many commits per round: hand back to the grid-wide rounds).
 __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b, const uint32_t* codes,
-                              const unsigned long long n_edges) {
+                              const unsigned long long n_edges, const int wtag) {
   const float inv_scale = (float)(1.0 / (double)bucket_scale());
   const float edge_w = (float)b * inv_scale;
   const int mins = p.min_region_size;
@@ -672,8 +683,9 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
         const RegionRec& A = As[q];
         const RegionRec& B = Bs[q];
         bool done = false;
-        if (k == 2 && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        else if (k == 3 && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+        // the other side is a hub whose decision-relevant state cannot change in this window (see run_bucket)
+        if (k == 2 && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
+        else if (k == 3 && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         if (done) {
           p.done[S.pos[i]] = 1;
           S.code[i] = kDone;
@@ -740,211 +752,498 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
   }
 }
 
-// counters: [0] live count of buffer A, [1] of buffer B, [2] round epoch, [3] bucket finished flag
-// live entry = 4 words: code, ru, rv, position in the bucket; live_aux[slot] = cluster root (round 0)
+// ---------------------------------------------------------------------------------------------
+// Window certification.  The pending edges of a bucket are processed in consecutive position
+// windows (positions = reference order).  For the edges of one window, with the exact state at
+// the window start, the kernel proves for most of them what the serial scan will do, whatever
+// the order inside the window:
+//   * "atoms" are the current roots; an atom of >= min_region_size voxels is a HUB, the rest is
+//     small.  Small atoms joined by window edges form SUB-CLUSTERS (lock-free union-find).
+//   * a sub-cluster of total mass < min_region_size that touches exactly one hub is absorbed by
+//     it for sure: every edge between two regions of which one is small ends in a merge
+//     (segmentation_graph.h:375-440: regular merge, or small-region merge after a failed test),
+//     and the hub, being the larger side, keeps its own flag.  The only open question is whether
+//     an un-finalised hub fails a test on the way (it would become finalised).  The hub's mean
+//     stays within  Delta = R M / (S + M)  of its value at the window start (R = max colour
+//     distance of the atoms it can absorb in this window, M = their total size, S = its own
+//     size), and every region it can meet has its mean within R of it, so R + Delta <
+//     threshold certifies that no test fails: the hub is FROZEN (its decision-relevant state --
+//     big, flag, constraint -- cannot change in this window).  Finalised hubs are frozen by
+//     definition (they only absorb small regions, no test is evaluated against them).
+//   * a sub-cluster whose members are all un-finalised with a colour hull smaller than the
+//     threshold merges completely (every partial mean stays inside the hull), alone or together
+//     with its single un-finalised frozen hub.
+//   * everything else (sub-clusters between two hubs, hubs near a failing test, constraint
+//     conflicts, big-big tests) is left to the ordered rounds below, where a frozen hub may absorb
+//     a small region as soon as the edge is that region's next edge.
+// Windows that leave too many uncertified edges are halved and retried (a shorter window means a
+// smaller drift bound); a live edge between two hubs ends the window in front of it and is
+// executed alone.  Bulk merges compute the size-weighted mean from 64-bit fixed-point sums.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScFin = 1;        // a member is finalised
+constexpr int kScConMulti = 2;   // members / absorbable atoms carry different constraint ids
+constexpr int kScHubs3 = 4;      // sub-cluster touches more than two hubs
+constexpr int kScUnc = 8;        // hub: may meet another un-finalised hub through a shared sub-cluster
+constexpr unsigned long long kWindowTarget = 1ull << 18;   // live edges aimed at per window
+constexpr unsigned long long kWindowMin = 4096;            // windows are not halved below this many raw edges
+constexpr unsigned long long kResidualSplit = 4096;        // uncertified edges that trigger a halving
+
+__device__ __forceinline__ bool is_hub(const RegionRec& r, int mins) { return r.sz >= mins; }
+
+__device__ __forceinline__ NodeScratch load_sc(const NodeScratch* s) {
+  NodeScratch o;
+  const int4* q = reinterpret_cast<const int4*>(s);
+  const int4 a = q[0], b = q[1], c = q[2], d = q[3];
+  o.mn[0] = a.x; o.mn[1] = a.y; o.mn[2] = a.z; o.mx[0] = a.w;
+  o.mx[1] = b.x; o.mx[2] = b.y; o.flags = b.z; o.con = b.w;
+  o.mass = c.x; o.hub0 = c.y; o.hub1 = c.z; o.rbits = c.w;
+  o.num = ((unsigned long long)(unsigned)d.y << 32) | (unsigned)d.x; o.claim = d.z; o.frozen = d.w;
+  return o;
+}
+__device__ __forceinline__ void reset_sc(NodeScratch* s) {
+  int4* q = reinterpret_cast<int4*>(s);
+  q[0] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
+  q[1] = make_int4(0, 0, 0, kNoCon);
+  q[2] = make_int4(0, -1, -1, 0);
+  s->num = 0ull;                     // claim / frozen tags stay
+}
+
+struct WindowThr { float thr_m, con_thr; };
+
+// Is the decision-relevant state of hub H certified constant in this window?
+__device__ __forceinline__ bool hub_frozen_eval(const RegionRec& H, const NodeScratch& S, const WindowThr& t) {
+  if (S.flags & kScConMulti) return false;
+  int conset = H.con;
+  if (S.con != kNoCon) {
+    if (conset >= 0 && conset != S.con) return false;
+    conset = S.con;
+  }
+  const float R = __int_as_float(S.rbits);
+  const double M = (double)S.mass, Sz = (double)H.sz;
+  const float delta = (float)((double)R * M / (Sz + M)) * 1.0001f + 1e-7f;   // drift of the hub mean, see above
+  if (conset >= 0 && !(R + delta < t.con_thr)) return false;
+  if (!H.fin) {
+    if (S.flags & kScUnc) return false;
+    if (!(R + delta < t.thr_m)) return false;
+  }
+  return true;
+}
+
+// Is the sub-cluster with record S (root c) certified?  *target = node everything merges into.
+__device__ __forceinline__ bool subcluster_certified(const MergeParams& p, int c, const NodeScratch& S, const WindowThr& t,
+                                                     int mins, int* target) {
+  *target = c;
+  if (S.flags & (kScConMulti | kScHubs3)) return false;
+  const float dx = __int_as_float(S.mx[0]) - __int_as_float(S.mn[0]);
+  const float dy = __int_as_float(S.mx[1]) - __int_as_float(S.mn[1]);
+  const float dz = __int_as_float(S.mx[2]) - __int_as_float(S.mn[2]);
+  const float diam = sqrtf((dx * dx + dy * dy + dz * dz) * (1.0f / 3.0f));
+  if (S.con != kNoCon && !(diam < t.con_thr)) return false;
+  if (S.hub0 < 0) return !(S.flags & kScFin) && diam < t.thr_m;
+  if (S.hub1 >= 0) return false;
+  const RegionRec H = load_rec(&p.rec[S.hub0]);
+  const NodeScratch HS = load_sc(&p.hull[S.hub0]);
+  if (!hub_frozen_eval(H, HS, t)) return false;
+  *target = S.hub0;
+  if (S.mass < mins) return true;
+  return !H.fin && !(S.flags & kScFin) && diam < t.thr_m;
+}
+
+// counters: [0] live count of buffer A, [1] of buffer B, [2] round epoch, [3] serial result flag,
+//           [4] first hub-hub position of the window, [5] uncertified edge count, [6] window tag
+// live entry = 4 words: code, ru, rv, position in the window
 template <class Bar, bool kIsGrid>
 __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, const unsigned tid, const unsigned nthr,
-                           const int b, const uint32_t* codes, const unsigned long long n_edges, unsigned epoch) {
+                           const int b, const uint32_t* bucket_codes, const unsigned long long bucket_edges) {
   const float inv_scale = (float)(1.0 / (double)bucket_scale());   // segmentation_graph.h:348
   const float edge_w = (float)b * inv_scale;
   const bool force_bucket = edge_w < p.force_merge_weight;
-  const float safe_thr = (force_bucket ? 0.2f : 0.05f) * 0.999f;
+  WindowThr wt;
+  wt.thr_m = (force_bucket ? 0.2f : 0.05f) * 0.999f - 2e-5f;
+  wt.con_thr = force_bucket ? wt.thr_m : (0.15f * 0.999f - 2e-5f);
   const int mins = p.min_region_size;
-  unsigned buf = 0;                 // index of the buffer P1 writes to
-  bool first_round = true;
-  unsigned long long n_src = n_edges, prev_live = n_edges;
-  // done flags of this bucket
-  for (unsigned long long i = tid; i < n_edges; i += nthr) p.done[i] = 0;
-  bar.sync();
+  unsigned epoch = (unsigned)(*((volatile unsigned long long*)&p.counters[2]));
+  int wtag = (int)(*((volatile unsigned long long*)&p.counters[6]));
+  bar.sync();                                   // everybody has read the persistent counters
+  unsigned long long w0 = 0;
+  unsigned long long raw = min(bucket_edges, kWindowTarget);
   unsigned long long guard = 0;
-  while (true) {
-    if (++guard > (1ull << 22)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } break; }
-    uint32_t* dst = buf ? p.live_b : p.live_a;
-    const uint32_t* src = buf ? p.live_a : p.live_b;
-    unsigned long long* dst_cnt = &p.counters[buf];
-    const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - epoch)) << 32;
-    // ---- P1: find roots, drop inert edges, reserve ----
-    for (unsigned long long i = tid; i < n_src; i += nthr) {
-      uint32_t code, pos;
-      if (first_round) { code = codes[i]; pos = (uint32_t)i; }
-      else { const uint4 e = reinterpret_cast<const uint4*>(src)[i]; code = e.x; pos = e.w; }
-      if (code == kDone || p.done[pos]) continue;
-      int u, v;
-      decode_edge(p, code, u, v);
-      const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-      bool drop = (ru == rv);
-      if (!drop) {
-        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-        const bool both_con = (A.con >= 0 && B.con >= 0);
-        drop = (both_con && A.con != B.con)                                   // kept for ever
-               || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);   // inert
-      }
-      if (drop) { p.done[pos] = 1; continue; }
-      const unsigned long long slot = atomicAdd(dst_cnt, 1ull);
-      if (slot < p.live_cap) {
-        reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
-        atomicMin(&p.res[ru], key_hi | code);
-        atomicMin(&p.res[rv], key_hi | code);
-      }
-    }
-    bar.sync();
-    unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
-    if (n_live > p.live_cap) n_live = p.live_cap;   // cannot happen: cap = largest bucket
-    if (n_live == 0) break;
-    if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
-    if (first_round && tid == 0) p.stats[4] = n_live;
-    // ---- chain regime: let block 0 finish (or advance) the bucket in serial window mode ----
-    if (!first_round && prev_live - n_live < kSerialSwitch) {
-      if (kIsGrid) {
-        if (blockIdx.x == 0) {
-          const bool fin = serial_rounds(p, S, b, codes, n_edges);
-          if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+  while (w0 < bucket_edges) {
+    unsigned long long n_edges = min(raw, bucket_edges - w0);
+    const uint32_t* codes = bucket_codes + w0;
+    bool allow_hubhub_cut = true;
+    unsigned long long n_live = 0;
+    uint32_t* dst = p.live_a;
+    // ---------------- window set-up: prune, reserve, cut at the first hub-hub edge, certify ----------------
+    while (true) {
+      if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
+      ++wtag;
+      for (unsigned long long i = tid; i < n_edges; i += nthr) p.done[i] = 0;
+      if (tid == 0) { p.counters[0] = 0ull; p.counters[1] = 0ull; p.counters[4] = ~0ull; p.counters[5] = 0ull; }
+      bar.sync();
+      // ---- P1: roots, inert edges, first hub-hub edge ----
+      for (unsigned long long i = tid; i < n_edges; i += nthr) {
+        const uint32_t code = codes[i];
+        int u, v;
+        decode_edge(p, code, u, v);
+        const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+        bool drop = (ru == rv);
+        bool hubhub = false;
+        if (!drop) {
+          const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+          const bool both_con = (A.con >= 0 && B.con >= 0);
+          drop = (both_con && A.con != B.con)
+                 || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);   // inert
+          hubhub = !drop && A.sz >= mins && B.sz >= mins;
         }
-      } else {
-        const bool fin = serial_rounds(p, S, b, codes, n_edges);
-        if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
-      }
-      if (tid == 0) trace(p, 3, 2);
-      bar.sync();
-      if (tid == 0) trace(p, 3, 3);
-      const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
-      if (finished) break;
-      // productive again: next grid round re-reads this round's list (done flags filter it)
-      if (tid == 0) p.counters[buf ^ 1] = 0ull;
-      bar.sync();
-      n_src = n_live;
-      prev_live = ~0ull >> 1;       // force at least one grid round
-      buf ^= 1;
-      ++epoch;
-      continue;
-    }
-    prev_live = n_live;
-    if (first_round) {
-      // ---- P2a: clusters of this bucket's pending edges ----
-      for (unsigned long long i = tid; i < n_live; i += nthr) {
-        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        cl_union(p.cl, (int)e.y, (int)e.z);
+        if (drop) { p.done[i] = 1; continue; }
+        if (hubhub) atomicMin(&p.counters[4], i);
+        const unsigned long long slot = atomicAdd(&p.counters[0], 1ull);
+        if (slot < p.live_cap) {
+          reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, (uint32_t)i);
+        }
       }
       bar.sync();
-      // ---- P2b: per-cluster colour hull / flags ----
+      n_live = *((volatile unsigned long long*)&p.counters[0]);
+      if (n_live > p.live_cap) n_live = p.live_cap;   // cannot happen: cap = largest bucket
+      const unsigned long long hh = *((volatile unsigned long long*)&p.counters[4]);
+      if (n_live == 0) break;
+      if (allow_hubhub_cut && hh < n_edges && n_edges > 1) {
+        // a real big-big decision: the window ends in front of it; the edge then runs alone
+        n_edges = (hh == 0) ? 1 : hh;
+        allow_hubhub_cut = (hh != 0);
+        ++epoch;
+        bar.sync();
+        continue;
+      }
+      if (n_edges == 1) break;                        // a single edge: the ordered round executes it exactly
+      // ---- C1: sub-clusters of small atoms ----
       for (unsigned long long i = tid; i < n_live; i += nthr) {
         const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        const int c = cl_find(p.cl, (int)e.y);
-        p.live_aux[i] = (uint32_t)c;
-        int* hl = p.hull + (size_t)c * 8;
+        const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
+        if (sa < mins && sb < mins) cl_union(p.cl, (int)e.y, (int)e.z);
+      }
+      bar.sync();
+      // ---- C2: sub-cluster records (once per atom) and hub adjacency ----
+      // Atoms of one sub-cluster sit next to each other in reference order: lanes that update the
+      // same record are combined with __match_any_sync / __reduce_*_sync, one atomic per group.
+      const int tag_a = 2 * wtag, tag_b = 2 * wtag + 1;
+      const unsigned lane = threadIdx.x & 31u;
+      for (unsigned long long i0 = tid - lane; i0 < n_live; i0 += nthr) {
+        const unsigned long long i = i0 + lane;
+        const bool in = i < n_live;
+        uint4 e = make_uint4(kDone, 0u, 0u, 0u);
+        if (in) e = reinterpret_cast<const uint4*>(dst)[i];
+        int hub = -1, sub = -1;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          bool valid = false;
+          int c = -1;
+          RegionRec R;
+          R.sz = 0; R.con = -1; R.d0 = R.d1 = R.d2 = 0.f; R.fin = 0; R.pad0 = R.pad1 = 0;
+          if (in) {
+            const int r = s ? (int)e.z : (int)e.y;
+            R = load_rec(&p.rec[r]);
+            if (R.sz >= mins) hub = r;
+            else {
+              c = cl_find_compress(p.cl, r);
+              sub = c;
+              valid = atomicExch(&p.hull[r].claim, tag_a) != tag_a;
+            }
+          }
+          const unsigned act = __ballot_sync(0xffffffffu, valid);
+          if (valid) {
+            const unsigned peers = __match_any_sync(act, c);
+            const int m0 = __reduce_min_sync(peers, __float_as_int(R.d0)), x0 = __reduce_max_sync(peers, __float_as_int(R.d0));
+            const int m1 = __reduce_min_sync(peers, __float_as_int(R.d1)), x1 = __reduce_max_sync(peers, __float_as_int(R.d1));
+            const int m2 = __reduce_min_sync(peers, __float_as_int(R.d2)), x2 = __reduce_max_sync(peers, __float_as_int(R.d2));
+            const int mass = __reduce_add_sync(peers, R.sz);
+            const unsigned fin = __reduce_or_sync(peers, R.fin ? 1u : 0u);
+            NodeScratch* sc = &p.hull[c];
+            if (lane == (unsigned)(__ffs(peers) - 1)) {
+              atomicMin(&sc->mn[0], m0); atomicMax(&sc->mx[0], x0);
+              atomicMin(&sc->mn[1], m1); atomicMax(&sc->mx[1], x1);
+              atomicMin(&sc->mn[2], m2); atomicMax(&sc->mx[2], x2);
+              atomicAdd(&sc->mass, mass);
+              if (fin) atomicOr(&sc->flags, kScFin);
+            }
+            if (R.con >= 0) {
+              const int old = atomicCAS(&sc->con, kNoCon, R.con);
+              if (old != kNoCon && old != R.con) atomicOr(&sc->flags, kScConMulti);
+            }
+          }
+        }
+        if (hub >= 0 && sub >= 0) {
+          NodeScratch* sc = &p.hull[sub];
+          int old = *((volatile int*)&sc->hub0);
+          if (old == -1) old = atomicCAS(&sc->hub0, -1, hub);
+          if (old != -1 && old != hub) {
+            old = *((volatile int*)&sc->hub1);
+            if (old == -1) old = atomicCAS(&sc->hub1, -1, hub);
+            if (old != -1 && old != hub) atomicOr(&sc->flags, kScHubs3);
+          }
+        }
+      }
+      bar.sync();
+      // ---- C3: what every hub may absorb in this window (once per atom and hub) ----
+      for (unsigned long long i0 = tid - lane; i0 < n_live; i0 += nthr) {
+        const unsigned long long i = i0 + lane;
+        const bool in = i < n_live;
+        uint4 e = make_uint4(kDone, 0u, 0u, 0u);
+        if (in) e = reinterpret_cast<const uint4*>(dst)[i];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          bool valid = false;
+          RegionRec R;
+          R.sz = 0; R.con = -1; R.d0 = R.d1 = R.d2 = 0.f; R.fin = 0; R.pad0 = R.pad1 = 0;
+          NodeScratch SC;
+          SC.hub0 = SC.hub1 = -1; SC.flags = 0; SC.con = kNoCon;
+          if (in) {
+            const int r = s ? (int)e.z : (int)e.y;
+            R = load_rec(&p.rec[r]);
+            if (R.sz >= mins) {
+              // hub side of a hub-small edge: a sub-cluster with more than two hubs makes all of them uncertain
+              const int o = s ? (int)e.y : (int)e.z;
+              if (p.rec[o].sz < mins) {
+                const int c = cl_find(p.cl, o);
+                if ((p.hull[c].flags & kScHubs3) && !(p.hull[r].flags & kScUnc)) atomicOr(&p.hull[r].flags, kScUnc);
+              }
+            } else if (atomicExch(&p.hull[r].claim, tag_b) != tag_b) {
+              SC = load_sc(&p.hull[cl_find(p.cl, r)]);
+              valid = true;
+            }
+          }
+          bool both_open = false;
+          if (valid && SC.hub0 >= 0 && SC.hub1 >= 0) both_open = !p.rec[SC.hub0].fin && !p.rec[SC.hub1].fin;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int h = q ? SC.hub1 : SC.hub0;
+            const bool v = valid && h >= 0;
+            const unsigned act = __ballot_sync(0xffffffffu, v);
+            if (!v) continue;
+            const unsigned peers = __match_any_sync(act, h);
+            const RegionRec H = load_rec(&p.rec[h]);
+            const float d = raw_dist(H, R);
+            const int rmax = __reduce_max_sync(peers, __float_as_int(d));
+            const int mass = __reduce_add_sync(peers, R.sz);
+            NodeScratch* hs = &p.hull[h];
+            if (lane == (unsigned)(__ffs(peers) - 1)) {
+              atomicMax(&hs->rbits, rmax);
+              atomicAdd(&hs->mass, mass);
+            }
+            const int hflags = *((volatile int*)&hs->flags);
+            if ((both_open || (SC.flags & kScHubs3)) && !(hflags & kScUnc)) atomicOr(&hs->flags, kScUnc);   // a dynamic big-big test is possible
+            if (SC.flags & kScConMulti) { if (!(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti); }
+            else if (SC.con != kNoCon) {
+              int old = *((volatile int*)&hs->con);
+              if (old == kNoCon) old = atomicCAS(&hs->con, kNoCon, SC.con);
+              if (old != kNoCon && old != SC.con && !(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti);
+            }
+          }
+        }
+      }
+      bar.sync();
+      // ---- C4: count the edges the certificates do not cover ----
+      {
+        unsigned long long mine = 0;
+        for (unsigned long long i = tid; i < n_live; i += nthr) {
+          const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+          const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
+          bool cert = false;
+          if (sa < mins || sb < mins) {
+            const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
+            int target;
+            cert = subcluster_certified(p, c, load_sc(&p.hull[c]), wt, mins, &target);
+          }
+          if (!cert) ++mine;
+        }
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&p.counters[5], mine);
+      }
+      bar.sync();
+      const unsigned long long n_unc = *((volatile unsigned long long*)&p.counters[5]);
+      const bool split = (n_unc > kResidualSplit && n_edges > kWindowMin);
+      // ---- C5: apply the certified merges (or only reset the scratch when the window is halved) ----
+      for (unsigned long long i = tid; i < n_live; i += nthr) {
+        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+        if (split) continue;
+        const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;    // sizes are not folded before the next barrier
+        if (sa >= mins && sb >= mins) continue;
+        const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
+        int target;
+        const NodeScratch SC = load_sc(&p.hull[c]);
+        if (!subcluster_certified(p, c, SC, wt, mins, &target)) {
+          // the ordered rounds may let frozen hubs absorb: publish the certificate
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int h = q ? SC.hub1 : SC.hub0;
+            if (h < 0) continue;
+            if (p.hull[h].frozen != wtag && hub_frozen_eval(load_rec(&p.rec[h]), load_sc(&p.hull[h]), wt)) p.hull[h].frozen = wtag;
+          }
+          continue;
+        }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const int r = s ? (int)e.z : (int)e.y;
-          const RegionRec R = load_rec(&p.rec[r]);
-          atomicMin(&hl[0], __float_as_int(R.d0)); atomicMax(&hl[3], __float_as_int(R.d0));
-          atomicMin(&hl[1], __float_as_int(R.d1)); atomicMax(&hl[4], __float_as_int(R.d1));
-          atomicMin(&hl[2], __float_as_int(R.d2)); atomicMax(&hl[5], __float_as_int(R.d2));
-          if (R.fin) atomicOr(&hl[6], 1);
-          if (R.con >= 0) { atomicMin(&hl[7], R.con); atomicOr(&hl[6], 2); }
-        }
-      }
-      bar.sync();
-      // ---- P2c: which clusters are safe (any objecting edge makes its cluster ordered) ----
-      for (unsigned long long i = tid; i < n_live; i += nthr) {
-        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        const int c = (int)p.live_aux[i];
-        int* hl = p.hull + (size_t)c * 8;
-        const int flags = hl[6];
-        bool safe = (flags & 1) == 0;
-        if (safe && (flags & 2)) {
-          // constrained members must all carry one id: every root is an endpoint of some edge
-          const RegionRec A = load_rec(&p.rec[(int)e.y]), B = load_rec(&p.rec[(int)e.z]);
-          const int cmin = hl[7];
-          if ((A.con >= 0 && A.con != cmin) || (B.con >= 0 && B.con != cmin)) safe = false;
-        }
-        if (safe) {
-          const float dx = __int_as_float(hl[3]) - __int_as_float(hl[0]);
-          const float dy = __int_as_float(hl[4]) - __int_as_float(hl[1]);
-          const float dz = __int_as_float(hl[5]) - __int_as_float(hl[2]);
-          const float diam = sqrtf((dx * dx + dy * dy + dz * dz) * (1.0f / 3.0f));
-          safe = diam < safe_thr;
-        }
-        if (!safe) atomicOr(&hl[6], 8);
-      }
-      bar.sync();
-      // ---- P2d: merge safe clusters in bulk ----
-      for (unsigned long long i = tid; i < n_live; i += nthr) {
-        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        const int c = (int)p.live_aux[i];
-        const int* hl = p.hull + (size_t)c * 8;
-        if (hl[6] & 8) continue;             // unsafe cluster -> ordered rounds
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int r = s ? (int)e.z : (int)e.y;
-          if (r == c) continue;
-          const int old = atomicExch(&p.parent[r], c);
+          if (r == target) continue;
+          const int old = atomicExch(&p.parent[r], target);
           if (old == r) {
             const RegionRec R = load_rec(&p.rec[r]);
-            if (R.con >= 0) atomicMax(&p.rec[c].con, R.con);
-            acc_add(p.acc, c, R);
+            if (R.con >= 0) atomicMax(&p.rec[target].con, R.con);
+            acc_add(p.acc, target, R);
           }
         }
         reinterpret_cast<uint4*>(dst)[i].x = kDone;
         p.done[e.w] = 1;
       }
       bar.sync();
-    }
-    if (tid == 0) trace(p, 3, 10);
-    // ---- P3: commit (strict owners + absorption by finalised big regions); reset cluster scratch ----
-    for (unsigned long long i = tid; i < n_live; i += nthr) {
-      const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-      const int ru = (int)e.y, rv = (int)e.z;
-      if (first_round) {
-        const int c = (int)p.live_aux[i];
-        int* hl = p.hull + (size_t)c * 8;
-        reinterpret_cast<int4*>(hl)[0] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
-        reinterpret_cast<int4*>(hl)[1] = make_int4(0, 0, 0, 0x7f7f7f7f);
-        p.cl[ru] = ru;
-        p.cl[rv] = rv;
+      // ---- C6: fold the bulk contributions, scratch back to idle ----
+      for (unsigned long long i = tid; i < n_live; i += nthr) {
+        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int r = s ? (int)e.z : (int)e.y;
+          acc_fold(p, r);
+          p.cl[r] = r;
+          reset_sc(&p.hull[r]);
+        }
       }
-      if (e.x == kDone) continue;
-      const unsigned long long key = key_hi | e.x;
-      const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
-      bool done = false;
-      if (own_u && own_v) {
-        exec_strict(p, ru, rv, edge_w, p.stats);
-        done = true;
-      } else if (own_u || own_v) {
-        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-        // x = the side this edge is the next edge of; hub = finalised region of >= min size
-        if (own_v && A.fin && A.sz >= mins && B.sz < mins && B.con < 0) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        else if (own_u && B.fin && B.sz >= mins && A.sz < mins && A.con < 0) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+      if (tid == 0) atomicAdd(&p.stats[5], 1ull);
+      if (!split) { if (tid == 0) { atomicAdd(&p.stats[6], n_unc); } break; }
+      n_edges = (n_edges + 1) / 2;
+      raw = n_edges;
+      ++epoch;
+      bar.sync();
+    }
+    const unsigned long long live_setup = n_live;
+    // ---------------- ordered rounds on what is left of the window ----------------
+    if (n_live != 0) {
+      // the certified merges changed roots: every round starts with a fresh prune / reserve pass;
+      // the first one reads the set-up's list (buffer A) and writes buffer B
+      unsigned buf = 1;
+      unsigned long long n_src = n_live, prev_live = ~0ull >> 1;
+      if (tid == 0) p.counters[1] = 0ull;
+      ++epoch;
+      bar.sync();
+      while (true) {
+        if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
+        const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - epoch)) << 32;
+        dst = buf ? p.live_b : p.live_a;
+        const uint32_t* src = buf ? p.live_a : p.live_b;
+        unsigned long long* dst_cnt = &p.counters[buf];
+        // ---- P1: find roots, drop inert edges, reserve ----
+        for (unsigned long long i = tid; i < n_src; i += nthr) {
+          const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
+          const uint32_t code = e0.x, pos = e0.w;
+          if (code == kDone || p.done[pos]) continue;
+          int u, v;
+          decode_edge(p, code, u, v);
+          const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+          bool drop = (ru == rv);
+          if (!drop) {
+            const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+            const bool both_con = (A.con >= 0 && B.con >= 0);
+            drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+          }
+          if (drop) { p.done[pos] = 1; continue; }
+          const unsigned long long slot = atomicAdd(dst_cnt, 1ull);
+          if (slot < p.live_cap) {
+            reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
+            atomicMin(&p.res[ru], key_hi | code);
+            atomicMin(&p.res[rv], key_hi | code);
+          }
+        }
+        bar.sync();
+        n_live = *((volatile unsigned long long*)dst_cnt);
+        if (n_live > p.live_cap) n_live = p.live_cap;
+        if (n_live == 0) break;
+        if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
+        // ---- chain regime: block 0 finishes (or advances) the window in serial window mode ----
+        if (prev_live - n_live < kSerialSwitch) {
+          if (kIsGrid) {
+            if (blockIdx.x == 0) {
+              const bool fin = serial_rounds(p, S, b, codes, n_edges, wtag);
+              if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+            }
+          } else {
+            const bool fin = serial_rounds(p, S, b, codes, n_edges, wtag);
+            if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+          }
+          bar.sync();
+          const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
+          if (finished) break;
+          // productive again: the next grid round re-reads this round's list (done flags filter it)
+          if (tid == 0) p.counters[buf ^ 1] = 0ull;
+          bar.sync();
+          n_src = n_live;
+          prev_live = ~0ull >> 1;       // force at least one grid round
+          buf ^= 1;
+          ++epoch;
+          continue;
+        }
+        prev_live = n_live;
+        // ---- P3: commit (strict owners + absorption by frozen hubs) ----
+        for (unsigned long long i = tid; i < n_live; i += nthr) {
+          const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+          const int ru = (int)e.y, rv = (int)e.z;
+          const unsigned long long key = key_hi | e.x;
+          const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
+          bool done = false;
+          if (own_u && own_v) {
+            exec_strict(p, ru, rv, edge_w, p.stats);
+            done = true;
+          } else if (own_u || own_v) {
+            const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+            // the edge is the next edge of the side it owns; the other side is a hub whose
+            // decision-relevant state cannot change in this window
+            if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
+              p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true;
+            } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
+              p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true;
+            }
+          }
+          if (done) {
+            reinterpret_cast<uint4*>(dst)[i].x = kDone;
+            p.done[e.w] = 1;
+          }
+        }
+        bar.sync();
+        // ---- P4: fold bulk contributions ----
+        for (unsigned long long i = tid; i < n_live; i += nthr) {
+          const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+          acc_fold(p, (int)e.y);
+          acc_fold(p, (int)e.z);
+        }
+        if (tid == 0) {
+          p.counters[buf ^ 1] = 0ull;          // the other buffer becomes the next destination
+          atomicAdd(&p.stats[0], 1ull);
+        }
+        bar.sync();
+        n_src = n_live;
+        buf ^= 1;
+        ++epoch;
       }
-      if (done) {
-        reinterpret_cast<uint4*>(dst)[i].x = kDone;
-        p.done[e.w] = 1;
+    }
+    // next window: aim at kWindowTarget live edges
+    w0 += n_edges;
+    {
+      const unsigned long long live0 = live_setup ? live_setup : 1;
+      unsigned long long next = raw;
+      if (n_edges >= raw) {   // the window was not cut short: adapt to the live density
+        if (live0 * 2 < kWindowTarget) next = raw * 2;
+        if (live0 * 8 < kWindowTarget) next = raw * 4;
+        if (live0 > kWindowTarget * 2) next = raw / 2;
       }
+      raw = max(next, kWindowMin);
     }
-    bar.sync();
-    // ---- P4: fold bulk contributions ----
-    for (unsigned long long i = tid; i < n_live; i += nthr) {
-      const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-      acc_fold(p, (int)e.y);
-      acc_fold(p, (int)e.z);
-      if (first_round) acc_fold(p, (int)p.live_aux[i]);
-    }
-    if (tid == 0) {
-      p.counters[buf ^ 1] = 0ull;          // the other buffer becomes the next destination
-      atomicAdd(&p.stats[0], 1ull);
-    }
-    bar.sync();
-    // next round reads what this round wrote
-    n_src = n_live;
-    first_round = false;
-    buf ^= 1;
     ++epoch;
+    bar.sync();
   }
   if (tid == 0) {
     p.counters[0] = 0ull;
     p.counters[1] = 0ull;
     p.counters[2] = (unsigned long long)(epoch + 1);
-    // counters[3] (serial result) is rewritten before every barrier it is read after: never reset here
-    // (a reset could overtake blocks that have not read it yet)
+    p.counters[6] = (unsigned long long)(wtag + 1);
   }
 }
 
@@ -958,13 +1257,12 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
   for (int b = 0; b < kNumBuckets; ++b) {
     const unsigned long long s0 = p.bucket_start[b], s1 = p.bucket_start[b + 1];
     if (s1 == s0) continue;
-    const unsigned epoch = (unsigned)(*((volatile unsigned long long*)&p.counters[2]));
     unsigned long long t_bucket = 0;
     if (p.debug && gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_bucket));
     if (s1 - s0 <= kTailEdges) {
-      if (blockIdx.x == 0) run_bucket<BlockBar, false>(p, bbar, S, threadIdx.x, blockDim.x, b, p.codes + s0, s1 - s0, epoch);
+      if (blockIdx.x == 0) run_bucket<BlockBar, false>(p, bbar, S, threadIdx.x, blockDim.x, b, p.codes + s0, s1 - s0);
     } else {
-      run_bucket<GridBar, true>(p, gbar, S, gtid, gn, b, p.codes + s0, s1 - s0, epoch);
+      run_bucket<GridBar, true>(p, gbar, S, gtid, gn, b, p.codes + s0, s1 - s0);
     }
     gbar.sync();
     if (p.debug && gtid == 0) {
@@ -973,21 +1271,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
       p.debug[b * 4 + 0] = t1 - t_bucket;
       p.debug[b * 4 + 1] = p.stats[0];
       p.debug[b * 4 + 2] = s1 - s0;
-      p.debug[b * 4 + 3] = p.stats[4];
+      p.debug[b * 4 + 3] = p.stats[5];
     }
   }
-}
-
-size_t merge_scratch_bytes(int w, int h, int slots, unsigned long long max_bucket_edges) {
-  const size_t n = (size_t)w * h * slots;
-  size_t b = 0;
-  b += n * sizeof(unsigned long long);        // res
-  b += n * 4 * sizeof(unsigned long long);    // acc
-  b += n * sizeof(int);                       // cl
-  b += n * 8 * sizeof(int);                   // hull
-  b += 2 * max_bucket_edges * 16;             // live buffers
-  b += 16 * sizeof(unsigned long long);       // counters + stats
-  return b + 4096;
 }
 
 __global__ void init_nodes_kernel(const float* __restrict__ frame, const int* __restrict__ con_ids, int base,

@@ -355,15 +355,18 @@ int launch_init_iota(int* p, long long n, cudaStream_t s) {
   VSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
-// hull scratch of the merge kernel: [min0,min1,min2 | max0,max1,max2 | flags | conmin]
-__global__ void init_hull_kernel(int4* hull, long long n) {
+// certification scratch of the merge kernel (common.cuh: NodeScratch), idle state
+__global__ void init_hull_kernel(NodeScratch* sc, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    hull[2 * i] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
-    hull[2 * i + 1] = make_int4(0, 0, 0, 0x7f7f7f7f);
+    int4* q = reinterpret_cast<int4*>(&sc[i]);
+    q[0] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
+    q[1] = make_int4(0, 0, 0, kNoCon);
+    q[2] = make_int4(0, -1, -1, 0);
+    q[3] = make_int4(0, 0, 0, 0);
   }
 }
-int launch_init_hull(int* hull, long long n_nodes, cudaStream_t s) {
-  init_hull_kernel<<<148 * 4, 256, 0, s>>>((int4*)hull, n_nodes);
+int launch_init_hull(NodeScratch* hull, long long n_nodes, cudaStream_t s) {
+  init_hull_kernel<<<148 * 8, 256, 0, s>>>(hull, n_nodes);
   VSB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -19,7 +19,7 @@ int launch_neighbor_pairs(const int* roots, const int* labels, int w, int h, int
                           unsigned long long* table, unsigned table_cap_pow2, unsigned long long* out,
                           unsigned long long* out_count, unsigned long long out_cap, cudaStream_t s);
 int launch_fill_i32(int* p, int value, long long n, cudaStream_t s);
-int launch_init_hull(int* hull, long long n_nodes, cudaStream_t s);
+int launch_init_hull(NodeScratch* hull, long long n_nodes, cudaStream_t s);
 int launch_init_iota(int* p, long long n, cudaStream_t s);
 
 }  // namespace vsb
