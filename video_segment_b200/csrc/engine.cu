@@ -109,7 +109,7 @@ struct vsb200_dense {
 void vsb200_dense::release() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_bgr); F(d_pre_scratch); F(d_flows); F(d_codes); F(d_bstart); F(d_sort_scratch); F(d_parent); F(d_rec);
-  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_aux); F(mp.done); F(mp.counters);
+  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_aux); F(mp.done); F(mp.counters); F(mp.debug);
   F(d_labels); F(d_roots); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
   F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
   F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
@@ -487,7 +487,26 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   mp.codes = d_codes; mp.bucket_start = d_bstart; mp.parent = d_parent; mp.rec = d_rec;
   mp.live_cap = live_cap_alloc;
   ENG_CUDA(cudaMemsetAsync(mp.stats, 0, 8 * 8, stream));
+  const char* dbg_path = getenv("VSB200_MERGE_DEBUG");       // per-bucket profile of every chunk (development tap)
+  if (dbg_path && !mp.debug) ENG_CUDA(cudaMalloc(&mp.debug, (kNumBuckets * 4 + 16) * 8));
+  if (mp.debug) ENG_CUDA(cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 16) * 8, stream));
   ENG_RC(launch_merge(mp, stream));
+  if (mp.debug && dbg_path) {
+    std::vector<unsigned long long> dbg(kNumBuckets * 4 + 16);
+    ENG_CUDA(cudaMemcpyAsync(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost, stream));
+    ENG_CUDA(cudaStreamSynchronize(stream));
+    const std::string path = std::string(dbg_path) + ".chunk" + std::to_string(chunk_id);
+    if (FILE* f = fopen(path.c_str(), "w")) {
+      unsigned long long prev_r = 0, prev_w = 0;
+      for (int b = 0; b < kNumBuckets; ++b) {
+        if (dbg[b * 4 + 2] == 0) continue;
+        fprintf(f, "%d edges %llu windows %llu rounds %llu us %.1f\n", b, dbg[b * 4 + 2], dbg[b * 4 + 3] - prev_w,
+                dbg[b * 4 + 1] - prev_r, dbg[b * 4 + 0] / 1000.0);
+        prev_r = dbg[b * 4 + 1]; prev_w = dbg[b * 4 + 3];
+      }
+      fclose(f);
+    }
+  }
   stats[7] += 1;
   if (constrained_chunk) ENG_RC(merge_constrained_regions(slots));
   cudaEventRecord(ev[2], stream);

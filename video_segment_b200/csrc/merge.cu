@@ -784,11 +784,22 @@ constexpr int kScFin = 1;        // a member is finalised
 constexpr int kScConMulti = 2;   // members / absorbable atoms carry different constraint ids
 constexpr int kScHubs3 = 4;      // sub-cluster touches more than two hubs
 constexpr int kScUnc = 8;        // hub: may meet another un-finalised hub through a shared sub-cluster
+constexpr int kScUncAny = 16;    // hub: may meet a hub with the same constraint id through a shared sub-cluster (flags do not matter)
 constexpr unsigned long long kWindowTarget = 1ull << 18;   // live edges aimed at per window
 constexpr unsigned long long kWindowMin = 4096;            // windows are not halved below this many raw edges
 constexpr unsigned long long kResidualSplit = 4096;        // uncertified edges that trigger a halving
+constexpr int kP1U = 8;                                     // edges per thread in flight in the prune pass
 
-__device__ __forceinline__ bool is_hub(const RegionRec& r, int mins) { return r.sz >= mins; }
+// one atomic per converged group of lanes instead of one per live edge
+__device__ __forceinline__ unsigned long long warp_slot(unsigned long long* cnt) {
+  const unsigned act = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(act) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(cnt, (unsigned long long)__popc(act));
+  base = __shfl_sync(act, base, leader);
+  return base + __popc(act & ((1u << lane) - 1u));
+}
 
 __device__ __forceinline__ NodeScratch load_sc(const NodeScratch* s) {
   NodeScratch o;
@@ -812,11 +823,13 @@ struct WindowThr { float thr_m, con_thr; };
 
 // Is the decision-relevant state of hub H certified constant in this window?
 __device__ __forceinline__ bool hub_frozen_eval(const RegionRec& H, const NodeScratch& S, const WindowThr& t) {
-  if (S.flags & kScConMulti) return false;
+  // a constrained hub keeps its id whatever it meets (merging with another id never happens); an
+  // unconstrained hub takes the id of the first constrained region it absorbs, so two ids make it order dependent
+  if (S.flags & kScUncAny) return false;
   int conset = H.con;
-  if (S.con != kNoCon) {
-    if (conset >= 0 && conset != S.con) return false;
-    conset = S.con;
+  if (conset < 0) {
+    if (S.flags & kScConMulti) return false;
+    if (S.con != kNoCon) conset = S.con;
   }
   const float R = __int_as_float(S.rbits);
   const double M = (double)S.mass, Sz = (double)H.sz;
@@ -843,6 +856,7 @@ __device__ __forceinline__ bool subcluster_certified(const MergeParams& p, int c
   if (S.hub1 >= 0) return false;
   const RegionRec H = load_rec(&p.rec[S.hub0]);
   const NodeScratch HS = load_sc(&p.hull[S.hub0]);
+  if (H.con >= 0 && S.con != kNoCon && S.con != H.con) return false;      // foreign id: those edges are kept, the rest races
   if (!hub_frozen_eval(H, HS, t)) return false;
   *target = S.hub0;
   if (S.mass < mins) return true;
@@ -878,29 +892,64 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     while (true) {
       if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
       ++wtag;
-      for (unsigned long long i = tid; i < n_edges; i += nthr) p.done[i] = 0;
       if (tid == 0) { p.counters[0] = 0ull; p.counters[1] = 0ull; p.counters[4] = ~0ull; p.counters[5] = 0ull; }
       bar.sync();
-      // ---- P1: roots, inert edges, first hub-hub edge ----
-      for (unsigned long long i = tid; i < n_edges; i += nthr) {
-        const uint32_t code = codes[i];
-        int u, v;
-        decode_edge(p, code, u, v);
-        const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-        bool drop = (ru == rv);
-        bool hubhub = false;
-        if (!drop) {
-          const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-          const bool both_con = (A.con >= 0 && B.con >= 0);
-          drop = (both_con && A.con != B.con)
-                 || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);   // inert
-          hubhub = !drop && A.sz >= mins && B.sz >= mins;
+      // ---- P1: roots, inert edges, first hub-hub edge.  kP1U edges per thread are in flight
+      // together (the pass is bound by the latency of the dependent parent / record loads) ----
+      for (unsigned long long i0 = tid; i0 < n_edges; i0 += (unsigned long long)nthr * kP1U) {
+        uint32_t code[kP1U];
+        int us[kP1U], vs[kP1U], pu[kP1U], pv[kP1U], rus[kP1U], rvs[kP1U];
+        bool in[kP1U];
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          const unsigned long long i = i0 + (unsigned long long)k * nthr;
+          in[k] = i < n_edges;
+          code[k] = in[k] ? __ldg(&codes[i]) : 0u;
         }
-        if (drop) { p.done[i] = 1; continue; }
-        if (hubhub) atomicMin(&p.counters[4], i);
-        const unsigned long long slot = atomicAdd(&p.counters[0], 1ull);
-        if (slot < p.live_cap) {
-          reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, (uint32_t)i);
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          us[k] = 0; vs[k] = 0;
+          if (in[k]) decode_edge(p, code[k], us[k], vs[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) { pu[k] = p.parent[us[k]]; pv[k] = p.parent[vs[k]]; }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          rus[k] = (pu[k] == us[k]) ? us[k] : uf_find(p.parent, pu[k]);
+          rvs[k] = (pv[k] == vs[k]) ? vs[k] : uf_find(p.parent, pv[k]);
+          if (in[k]) {
+            if (pu[k] != us[k] && rus[k] != pu[k]) p.parent[us[k]] = rus[k];     // path compression
+            if (pv[k] != vs[k] && rvs[k] != pv[k]) p.parent[vs[k]] = rvs[k];
+          }
+        }
+        int4 a0[kP1U], b0[kP1U];      // first halves of the two records (sz, con, d0, d1) and fin words
+        int af[kP1U], bf[kP1U];
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          const bool need = in[k] && rus[k] != rvs[k];
+          const int ia = need ? rus[k] : 0, ib = need ? rvs[k] : 0;
+          a0[k] = reinterpret_cast<const int4*>(&p.rec[ia])[0]; af[k] = p.rec[ia].fin;
+          b0[k] = reinterpret_cast<const int4*>(&p.rec[ib])[0]; bf[k] = p.rec[ib].fin;
+        }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          if (!in[k]) continue;
+          const unsigned long long i = i0 + (unsigned long long)k * nthr;
+          bool drop = (rus[k] == rvs[k]);
+          bool hubhub = false;
+          if (!drop) {
+            const int asz = a0[k].x, acon = a0[k].y, bsz = b0[k].x, bcon = b0[k].y;
+            const bool both_con = (acon >= 0 && bcon >= 0);
+            drop = (both_con && acon != bcon)
+                   || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
+            hubhub = !drop && asz >= mins && bsz >= mins;
+          }
+          p.done[i] = drop ? 1 : 0;                // done flags of the window are (re)written here
+          if (drop) continue;
+          if (hubhub) atomicMin(&p.counters[4], i);
+          const unsigned long long slot = warp_slot(&p.counters[0]);
+          if (slot < p.live_cap)
+            reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
         }
       }
       bar.sync();
@@ -1006,15 +1055,20 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
               const int o = s ? (int)e.y : (int)e.z;
               if (p.rec[o].sz < mins) {
                 const int c = cl_find(p.cl, o);
-                if ((p.hull[c].flags & kScHubs3) && !(p.hull[r].flags & kScUnc)) atomicOr(&p.hull[r].flags, kScUnc);
+                if ((p.hull[c].flags & kScHubs3) && (p.hull[r].flags & (kScUnc | kScUncAny)) != (kScUnc | kScUncAny)) atomicOr(&p.hull[r].flags, R.con >= 0 ? (kScUnc | kScUncAny) : kScUnc);
               }
             } else if (atomicExch(&p.hull[r].claim, tag_b) != tag_b) {
               SC = load_sc(&p.hull[cl_find(p.cl, r)]);
               valid = true;
             }
           }
-          bool both_open = false;
-          if (valid && SC.hub0 >= 0 && SC.hub1 >= 0) both_open = !p.rec[SC.hub0].fin && !p.rec[SC.hub1].fin;
+          bool both_open = false, same_id = false;
+          if (valid && SC.hub0 >= 0 && SC.hub1 >= 0) {
+            const RegionRec H0 = load_rec(&p.rec[SC.hub0]), H1 = load_rec(&p.rec[SC.hub1]);
+            // two un-finalised hubs may meet through this sub-cluster (a big-big decision) unless their ids forbid it
+            both_open = !H0.fin && !H1.fin && !(H0.con >= 0 && H1.con >= 0 && H0.con != H1.con);
+            same_id = H0.con >= 0 && H0.con == H1.con;
+          }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int h = q ? SC.hub1 : SC.hub0;
@@ -1033,6 +1087,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             }
             const int hflags = *((volatile int*)&hs->flags);
             if ((both_open || (SC.flags & kScHubs3)) && !(hflags & kScUnc)) atomicOr(&hs->flags, kScUnc);   // a dynamic big-big test is possible
+            if ((same_id || ((SC.flags & kScHubs3) && H.con >= 0)) && !(hflags & kScUncAny)) atomicOr(&hs->flags, kScUncAny);
             if (SC.flags & kScConMulti) { if (!(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti); }
             else if (SC.con != kNoCon) {
               int old = *((volatile int*)&hs->con);
@@ -1146,7 +1201,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
           }
           if (drop) { p.done[pos] = 1; continue; }
-          const unsigned long long slot = atomicAdd(dst_cnt, 1ull);
+          const unsigned long long slot = warp_slot(dst_cnt);
           if (slot < p.live_cap) {
             reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
             atomicMin(&p.res[ru], key_hi | code);
