@@ -155,7 +155,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.hull = (NodeScratch*)dalloc(nodes * sizeof(NodeScratch));
     mp.live_a = (uint32_t*)dalloc(max_bucket * 16);
     mp.live_b = (uint32_t*)dalloc(max_bucket * 16);
-    mp.live_aux = (uint32_t*)dalloc(max_bucket * 4);
+    mp.live_c = (uint32_t*)dalloc(max_bucket * 16);
     mp.done = (unsigned char*)dalloc(max_bucket);
     mp.live_cap = max_bucket;
     mp.counters = (unsigned long long*)dalloc(16 * 8);
@@ -179,7 +179,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
         }
       });
     }
-    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.live_aux || !mp.done || !mp.counters) {
+    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.live_c || !mp.done || !mp.counters) {
       set_error("segment_chunk: out of device memory (merge workspace)");
       rc = VSB200_ERR_CUDA;
       break;

@@ -95,9 +95,9 @@ struct MergeParams {
   int* cl;                         // [nodes] scratch cluster union-find
   NodeScratch* hull;               // [nodes] certification scratch of the current window (idle between windows)
   unsigned char* done;             // [max bucket edges] per-position done flags of the current bucket
-  uint32_t* live_aux;              // [live_cap] cluster root of a live entry (first round of a bucket)
   uint32_t* live_a;                // live edge buffers: (code, ru, rv, position)
   uint32_t* live_b;
+  uint32_t* live_c;                // live_a = live list of the window, live_b / live_c = lists of the ordered rounds
   unsigned long long live_cap;     // in triples
   unsigned long long* counters;    // [8] device counters
   unsigned long long* stats;       // [8] rounds, commits, safe merges, ...

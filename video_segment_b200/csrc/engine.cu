@@ -109,7 +109,7 @@ struct vsb200_dense {
 void vsb200_dense::release() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_bgr); F(d_pre_scratch); F(d_flows); F(d_codes); F(d_bstart); F(d_sort_scratch); F(d_parent); F(d_rec);
-  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_aux); F(mp.done); F(mp.counters); F(mp.debug);
+  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_c); F(mp.done); F(mp.counters); F(mp.debug);
   F(d_labels); F(d_roots); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
   F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
   F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
@@ -473,10 +473,10 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     if (mp.live_b) cudaFree(mp.live_b);
     live_cap_alloc = max_bucket + max_bucket / 4;
     if (mp.done) cudaFree(mp.done);
-    if (mp.live_aux) cudaFree(mp.live_aux);
+    if (mp.live_c) cudaFree(mp.live_c);
     ENG_CUDA(cudaMalloc(&mp.live_a, live_cap_alloc * 16));
     ENG_CUDA(cudaMalloc(&mp.live_b, live_cap_alloc * 16));
-    ENG_CUDA(cudaMalloc(&mp.live_aux, live_cap_alloc * 4));
+    ENG_CUDA(cudaMalloc(&mp.live_c, live_cap_alloc * 16));
     ENG_CUDA(cudaMalloc(&mp.done, live_cap_alloc));
   }
   // ---------------- merge ----------------

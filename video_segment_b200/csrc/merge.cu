@@ -319,7 +319,7 @@ __device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsig
 // Returns true when the bucket is finished, false when the window became productive again
 // (many commits per round: hand back to the grid-wide rounds).
 __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b, const uint32_t* codes,
-                              const unsigned long long n_edges, const int wtag) {
+                              const unsigned long long n_edges, const int wtag, unsigned char* done_flags) {
   const float inv_scale = (float)(1.0 / (double)bucket_scale());
   const float edge_w = (float)b * inv_scale;
   const int mins = p.min_region_size;
@@ -339,7 +339,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
       const unsigned long long cur = S.cursor;
       if (wn >= kWin || cur >= n_edges) break;
       const unsigned long long pos = cur + tid;
-      const bool pend = (pos < n_edges) && (p.done[pos] == 0);
+      const bool pend = (pos < n_edges) && (done_flags[pos] == 0);
       unsigned total;
       const unsigned rank = block_rank(S, pend, &total);
       const unsigned room = (unsigned)(kWin - wn);
@@ -394,7 +394,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
           drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
         }
         if (drop) {
-          p.done[S.pos[i]] = 1;
+          done_flags[S.pos[i]] = 1;
           S.code[i] = kDone;
           S.ru[i] = 0xFFFFFFFFu; S.rv[i] = 0xFFFFFFFFu;
         } else {
@@ -455,7 +455,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
       if (items == 0) {
         // isolated head: nobody else touches its two roots this round
         exec_strict(p, (int)a, (int)b, edge_w, p.stats);
-        p.done[S.pos[i]] = 1;
+        done_flags[S.pos[i]] = 1;
         S.code[i] = kDone;
         atomicAdd(&S.commits, 1);
       } else {
@@ -517,7 +517,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
           if (res == 1) { p.parent[(int)hb] = (int)ha; hub_cur = (int)ha; H = A; merged = 1; }
           else if (res == 2) { p.parent[(int)ha] = (int)hb; hub_cur = (int)hb; H = B; merged = 1; }
           else { store_rec(&p.rec[(int)ha], A); store_rec(&p.rec[(int)hb], B); }
-          p.done[S.pos[i0]] = 1;
+          done_flags[S.pos[i0]] = 1;
           S.code[i0] = kDone;
         }
         merged = __shfl_sync(0xffffffffu, merged, 0);
@@ -593,7 +593,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
               }
               if (mine) {
                 if (is_leaf) p.parent[x] = hub_id;
-                p.done[S.pos[j]] = 1;
+                done_flags[S.pos[j]] = 1;
                 S.code[j] = kDone;
               }
               const int tot_sz = __shfl_sync(0xffffffffu, psz, 31);
@@ -642,7 +642,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
                   else if (res == 2) { p.parent[hub_cur] = other; hub_cur = other; H = L; }
                   else { store_rec(&p.rec[other], L); }
                 }
-                p.done[S.pos[jk]] = 1;
+                done_flags[S.pos[jk]] = 1;
                 S.code[jk] = kDone;
                 merged = 2;
               }
@@ -687,7 +687,7 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
         if (k == 2 && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
         else if (k == 3 && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         if (done) {
-          p.done[S.pos[i]] = 1;
+          done_flags[S.pos[i]] = 1;
           S.code[i] = kDone;
           atomicAdd(&S.commits, 1);
         }
@@ -882,413 +882,455 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
   unsigned long long w0 = 0;
   unsigned long long raw = min(bucket_edges, kWindowTarget);
   unsigned long long guard = 0;
+  uint32_t* const master = p.live_a;            // live list of the window (code, ru, rv, position)
+  const unsigned lane = threadIdx.x & 31u;
   while (w0 < bucket_edges) {
-    unsigned long long n_edges = min(raw, bucket_edges - w0);
+    const unsigned long long n_edges = min(raw, bucket_edges - w0);
     const uint32_t* codes = bucket_codes + w0;
-    bool allow_hubhub_cut = true;
-    unsigned long long n_live = 0;
-    uint32_t* dst = p.live_a;
-    // ---------------- window set-up: prune, reserve, cut at the first hub-hub edge, certify ----------------
-    while (true) {
+    if (tid == 0) { p.counters[0] = 0ull; p.counters[4] = ~0ull; }
+    bar.sync();
+    // ---- P1: roots, inert edges, first hub-hub edge.  kP1U edges per thread are in flight
+    // together (the pass is bound by the latency of the dependent parent / record loads) ----
+    for (unsigned long long i0 = tid; i0 < n_edges; i0 += (unsigned long long)nthr * kP1U) {
+      uint32_t code[kP1U];
+      int us[kP1U], vs[kP1U], pu[kP1U], pv[kP1U], rus[kP1U], rvs[kP1U];
+      bool in[kP1U];
+#pragma unroll
+      for (int k = 0; k < kP1U; ++k) {
+        const unsigned long long i = i0 + (unsigned long long)k * nthr;
+        in[k] = i < n_edges;
+        code[k] = in[k] ? __ldg(&codes[i]) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < kP1U; ++k) {
+        us[k] = 0; vs[k] = 0;
+        if (in[k]) decode_edge(p, code[k], us[k], vs[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kP1U; ++k) { pu[k] = p.parent[us[k]]; pv[k] = p.parent[vs[k]]; }
+#pragma unroll
+      for (int k = 0; k < kP1U; ++k) {
+        rus[k] = (pu[k] == us[k]) ? us[k] : uf_find(p.parent, pu[k]);
+        rvs[k] = (pv[k] == vs[k]) ? vs[k] : uf_find(p.parent, pv[k]);
+        if (in[k]) {
+          if (pu[k] != us[k] && rus[k] != pu[k]) p.parent[us[k]] = rus[k];     // path compression
+          if (pv[k] != vs[k] && rvs[k] != pv[k]) p.parent[vs[k]] = rvs[k];
+        }
+      }
+      int4 a0[kP1U], b0[kP1U];      // first halves of the two records (sz, con, d0, d1) and fin words
+      int af[kP1U], bf[kP1U];
+#pragma unroll
+      for (int k = 0; k < kP1U; ++k) {
+        const bool need = in[k] && rus[k] != rvs[k];
+        const int ia = need ? rus[k] : 0, ib = need ? rvs[k] : 0;
+        a0[k] = reinterpret_cast<const int4*>(&p.rec[ia])[0]; af[k] = p.rec[ia].fin;
+        b0[k] = reinterpret_cast<const int4*>(&p.rec[ib])[0]; bf[k] = p.rec[ib].fin;
+      }
+#pragma unroll
+      for (int k = 0; k < kP1U; ++k) {
+        if (!in[k]) continue;
+        const unsigned long long i = i0 + (unsigned long long)k * nthr;
+        bool drop = (rus[k] == rvs[k]);
+        bool hubhub = false;
+        if (!drop) {
+          const int asz = a0[k].x, acon = a0[k].y, bsz = b0[k].x, bcon = b0[k].y;
+          const bool both_con = (acon >= 0 && bcon >= 0);
+          drop = (both_con && acon != bcon)
+                 || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
+          hubhub = !drop && asz >= mins && bsz >= mins;
+        }
+        p.done[i] = drop ? 1 : 0;                // done flags of the window are (re)written here
+        if (drop) continue;
+        if (hubhub) atomicMin(&p.counters[4], i);
+        const unsigned long long slot = warp_slot(&p.counters[0]);
+        if (slot < p.live_cap)
+          reinterpret_cast<uint4*>(master)[slot] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
+      }
+    }
+    bar.sync();
+    unsigned long long n_master = *((volatile unsigned long long*)&p.counters[0]);
+    if (n_master > p.live_cap) n_master = p.live_cap;   // cannot happen: cap = largest bucket
+    unsigned long long hh = *((volatile unsigned long long*)&p.counters[4]);   // first live edge between two hubs
+    // ---------------- segments of the window: [seg_lo, seg_hi) in window positions ----------------
+    unsigned long long seg_lo = 0, seg_len = n_edges;
+    while (n_master != 0 && seg_lo < n_edges) {
       if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
-      ++wtag;
-      if (tid == 0) { p.counters[0] = 0ull; p.counters[1] = 0ull; p.counters[4] = ~0ull; p.counters[5] = 0ull; }
-      bar.sync();
-      // ---- P1: roots, inert edges, first hub-hub edge.  kP1U edges per thread are in flight
-      // together (the pass is bound by the latency of the dependent parent / record loads) ----
-      for (unsigned long long i0 = tid; i0 < n_edges; i0 += (unsigned long long)nthr * kP1U) {
-        uint32_t code[kP1U];
-        int us[kP1U], vs[kP1U], pu[kP1U], pv[kP1U], rus[kP1U], rvs[kP1U];
-        bool in[kP1U];
-#pragma unroll
-        for (int k = 0; k < kP1U; ++k) {
-          const unsigned long long i = i0 + (unsigned long long)k * nthr;
-          in[k] = i < n_edges;
-          code[k] = in[k] ? __ldg(&codes[i]) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < kP1U; ++k) {
-          us[k] = 0; vs[k] = 0;
-          if (in[k]) decode_edge(p, code[k], us[k], vs[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < kP1U; ++k) { pu[k] = p.parent[us[k]]; pv[k] = p.parent[vs[k]]; }
-#pragma unroll
-        for (int k = 0; k < kP1U; ++k) {
-          rus[k] = (pu[k] == us[k]) ? us[k] : uf_find(p.parent, pu[k]);
-          rvs[k] = (pv[k] == vs[k]) ? vs[k] : uf_find(p.parent, pv[k]);
-          if (in[k]) {
-            if (pu[k] != us[k] && rus[k] != pu[k]) p.parent[us[k]] = rus[k];     // path compression
-            if (pv[k] != vs[k] && rvs[k] != pv[k]) p.parent[vs[k]] = rvs[k];
-          }
-        }
-        int4 a0[kP1U], b0[kP1U];      // first halves of the two records (sz, con, d0, d1) and fin words
-        int af[kP1U], bf[kP1U];
-#pragma unroll
-        for (int k = 0; k < kP1U; ++k) {
-          const bool need = in[k] && rus[k] != rvs[k];
-          const int ia = need ? rus[k] : 0, ib = need ? rvs[k] : 0;
-          a0[k] = reinterpret_cast<const int4*>(&p.rec[ia])[0]; af[k] = p.rec[ia].fin;
-          b0[k] = reinterpret_cast<const int4*>(&p.rec[ib])[0]; bf[k] = p.rec[ib].fin;
-        }
-#pragma unroll
-        for (int k = 0; k < kP1U; ++k) {
-          if (!in[k]) continue;
-          const unsigned long long i = i0 + (unsigned long long)k * nthr;
-          bool drop = (rus[k] == rvs[k]);
-          bool hubhub = false;
-          if (!drop) {
-            const int asz = a0[k].x, acon = a0[k].y, bsz = b0[k].x, bcon = b0[k].y;
-            const bool both_con = (acon >= 0 && bcon >= 0);
-            drop = (both_con && acon != bcon)
-                   || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
-            hubhub = !drop && asz >= mins && bsz >= mins;
-          }
-          p.done[i] = drop ? 1 : 0;                // done flags of the window are (re)written here
-          if (drop) continue;
-          if (hubhub) atomicMin(&p.counters[4], i);
-          const unsigned long long slot = warp_slot(&p.counters[0]);
-          if (slot < p.live_cap)
-            reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
-        }
-      }
-      bar.sync();
-      n_live = *((volatile unsigned long long*)&p.counters[0]);
-      if (n_live > p.live_cap) n_live = p.live_cap;   // cannot happen: cap = largest bucket
-      const unsigned long long hh = *((volatile unsigned long long*)&p.counters[4]);
-      if (n_live == 0) break;
-      if (allow_hubhub_cut && hh < n_edges && n_edges > 1) {
-        // a real big-big decision: the window ends in front of it; the edge then runs alone
-        n_edges = (hh == 0) ? 1 : hh;
-        allow_hubhub_cut = (hh != 0);
-        ++epoch;
+      const unsigned long long seg_end = min(min(hh, n_edges), seg_lo + seg_len);   // a hub-hub edge ends the segment in front of it
+      unsigned long long seg_hi = seg_end;
+      bool have_live = false;
+      // ---- certification of [seg_lo, seg_hi), halving the segment while too much stays uncertified ----
+      while (seg_hi > seg_lo) {
+        ++wtag;
+        if (tid == 0) { p.counters[5] = 0ull; p.counters[7] = 0ull; }
         bar.sync();
-        continue;
-      }
-      if (n_edges == 1) break;                        // a single edge: the ordered round executes it exactly
-      // ---- C1: sub-clusters of small atoms ----
-      for (unsigned long long i = tid; i < n_live; i += nthr) {
-        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
-        if (sa < mins && sb < mins) cl_union(p.cl, (int)e.y, (int)e.z);
-      }
-      bar.sync();
-      // ---- C2: sub-cluster records (once per atom) and hub adjacency ----
-      // Atoms of one sub-cluster sit next to each other in reference order: lanes that update the
-      // same record are combined with __match_any_sync / __reduce_*_sync, one atomic per group.
-      const int tag_a = 2 * wtag, tag_b = 2 * wtag + 1;
-      const unsigned lane = threadIdx.x & 31u;
-      for (unsigned long long i0 = tid - lane; i0 < n_live; i0 += nthr) {
-        const unsigned long long i = i0 + lane;
-        const bool in = i < n_live;
-        uint4 e = make_uint4(kDone, 0u, 0u, 0u);
-        if (in) e = reinterpret_cast<const uint4*>(dst)[i];
-        int hub = -1, sub = -1;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          bool valid = false;
-          int c = -1;
-          RegionRec R;
-          R.sz = 0; R.con = -1; R.d0 = R.d1 = R.d2 = 0.f; R.fin = 0; R.pad0 = R.pad1 = 0;
-          if (in) {
-            const int r = s ? (int)e.z : (int)e.y;
-            R = load_rec(&p.rec[r]);
-            if (R.sz >= mins) hub = r;
-            else {
-              c = cl_find_compress(p.cl, r);
-              sub = c;
-              valid = atomicExch(&p.hull[r].claim, tag_a) != tag_a;
-            }
+#define VSB_IN_SEG(e) ((e).w >= seg_lo && (e).w < seg_hi && !p.done[(e).w])
+        // ---- C1: sub-clusters of small atoms ----
+        {
+          unsigned long long mine = 0;
+          for (unsigned long long i = tid; i < n_master; i += nthr) {
+            const uint4 e = reinterpret_cast<const uint4*>(master)[i];
+            if (!VSB_IN_SEG(e)) continue;
+            ++mine;
+            const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
+            if (sa < mins && sb < mins) cl_union(p.cl, (int)e.y, (int)e.z);
           }
-          const unsigned act = __ballot_sync(0xffffffffu, valid);
-          if (valid) {
-            const unsigned peers = __match_any_sync(act, c);
-            const int m0 = __reduce_min_sync(peers, __float_as_int(R.d0)), x0 = __reduce_max_sync(peers, __float_as_int(R.d0));
-            const int m1 = __reduce_min_sync(peers, __float_as_int(R.d1)), x1 = __reduce_max_sync(peers, __float_as_int(R.d1));
-            const int m2 = __reduce_min_sync(peers, __float_as_int(R.d2)), x2 = __reduce_max_sync(peers, __float_as_int(R.d2));
-            const int mass = __reduce_add_sync(peers, R.sz);
-            const unsigned fin = __reduce_or_sync(peers, R.fin ? 1u : 0u);
-            NodeScratch* sc = &p.hull[c];
-            if (lane == (unsigned)(__ffs(peers) - 1)) {
-              atomicMin(&sc->mn[0], m0); atomicMax(&sc->mx[0], x0);
-              atomicMin(&sc->mn[1], m1); atomicMax(&sc->mx[1], x1);
-              atomicMin(&sc->mn[2], m2); atomicMax(&sc->mx[2], x2);
-              atomicAdd(&sc->mass, mass);
-              if (fin) atomicOr(&sc->flags, kScFin);
-            }
-            if (R.con >= 0) {
-              const int old = atomicCAS(&sc->con, kNoCon, R.con);
-              if (old != kNoCon && old != R.con) atomicOr(&sc->flags, kScConMulti);
-            }
-          }
+          if (mine) atomicAdd(&p.counters[7], mine);
         }
-        if (hub >= 0 && sub >= 0) {
-          NodeScratch* sc = &p.hull[sub];
-          int old = *((volatile int*)&sc->hub0);
-          if (old == -1) old = atomicCAS(&sc->hub0, -1, hub);
-          if (old != -1 && old != hub) {
-            old = *((volatile int*)&sc->hub1);
-            if (old == -1) old = atomicCAS(&sc->hub1, -1, hub);
-            if (old != -1 && old != hub) atomicOr(&sc->flags, kScHubs3);
-          }
-        }
-      }
-      bar.sync();
-      // ---- C3: what every hub may absorb in this window (once per atom and hub) ----
-      for (unsigned long long i0 = tid - lane; i0 < n_live; i0 += nthr) {
-        const unsigned long long i = i0 + lane;
-        const bool in = i < n_live;
-        uint4 e = make_uint4(kDone, 0u, 0u, 0u);
-        if (in) e = reinterpret_cast<const uint4*>(dst)[i];
+        bar.sync();
+        if (*((volatile unsigned long long*)&p.counters[7]) == 0ull) break;      // nothing live in this segment
+        have_live = true;
+        // ---- C2: sub-cluster records (once per atom) and hub adjacency.  Atoms of one sub-cluster
+        // sit next to each other in reference order: lanes that update the same record are combined
+        // with __match_any_sync / __reduce_*_sync, one atomic per group. ----
+        const int tag_a = 2 * wtag, tag_b = 2 * wtag + 1;
+        for (unsigned long long i0 = tid - lane; i0 < n_master; i0 += nthr) {
+          const unsigned long long i = i0 + lane;
+          bool in = i < n_master;
+          uint4 e = make_uint4(kDone, 0u, 0u, 0u);
+          if (in) { e = reinterpret_cast<const uint4*>(master)[i]; in = VSB_IN_SEG(e); }
+          int hub = -1, sub = -1;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          bool valid = false;
-          RegionRec R;
-          R.sz = 0; R.con = -1; R.d0 = R.d1 = R.d2 = 0.f; R.fin = 0; R.pad0 = R.pad1 = 0;
-          NodeScratch SC;
-          SC.hub0 = SC.hub1 = -1; SC.flags = 0; SC.con = kNoCon;
-          if (in) {
-            const int r = s ? (int)e.z : (int)e.y;
-            R = load_rec(&p.rec[r]);
-            if (R.sz >= mins) {
-              // hub side of a hub-small edge: a sub-cluster with more than two hubs makes all of them uncertain
-              const int o = s ? (int)e.y : (int)e.z;
-              if (p.rec[o].sz < mins) {
-                const int c = cl_find(p.cl, o);
-                if ((p.hull[c].flags & kScHubs3) && (p.hull[r].flags & (kScUnc | kScUncAny)) != (kScUnc | kScUncAny)) atomicOr(&p.hull[r].flags, R.con >= 0 ? (kScUnc | kScUncAny) : kScUnc);
+          for (int s2 = 0; s2 < 2; ++s2) {
+            bool valid = false;
+            int c = -1;
+            RegionRec R;
+            R.sz = 0; R.con = -1; R.d0 = R.d1 = R.d2 = 0.f; R.fin = 0; R.pad0 = R.pad1 = 0;
+            if (in) {
+              const int r = s2 ? (int)e.z : (int)e.y;
+              R = load_rec(&p.rec[r]);
+              if (R.sz >= mins) hub = r;
+              else {
+                c = cl_find_compress(p.cl, r);
+                sub = c;
+                valid = atomicExch(&p.hull[r].claim, tag_a) != tag_a;
               }
-            } else if (atomicExch(&p.hull[r].claim, tag_b) != tag_b) {
-              SC = load_sc(&p.hull[cl_find(p.cl, r)]);
-              valid = true;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+              const unsigned peers = __match_any_sync(act, c);
+              const int m0 = __reduce_min_sync(peers, __float_as_int(R.d0)), x0 = __reduce_max_sync(peers, __float_as_int(R.d0));
+              const int m1 = __reduce_min_sync(peers, __float_as_int(R.d1)), x1 = __reduce_max_sync(peers, __float_as_int(R.d1));
+              const int m2 = __reduce_min_sync(peers, __float_as_int(R.d2)), x2 = __reduce_max_sync(peers, __float_as_int(R.d2));
+              const int mass = __reduce_add_sync(peers, R.sz);
+              const unsigned fin = __reduce_or_sync(peers, R.fin ? 1u : 0u);
+              NodeScratch* sc = &p.hull[c];
+              if (lane == (unsigned)(__ffs(peers) - 1)) {
+                atomicMin(&sc->mn[0], m0); atomicMax(&sc->mx[0], x0);
+                atomicMin(&sc->mn[1], m1); atomicMax(&sc->mx[1], x1);
+                atomicMin(&sc->mn[2], m2); atomicMax(&sc->mx[2], x2);
+                atomicAdd(&sc->mass, mass);
+                if (fin) atomicOr(&sc->flags, kScFin);
+              }
+              if (R.con >= 0) {
+                const int old = atomicCAS(&sc->con, kNoCon, R.con);
+                if (old != kNoCon && old != R.con) atomicOr(&sc->flags, kScConMulti);
+              }
             }
           }
-          bool both_open = false, same_id = false;
-          if (valid && SC.hub0 >= 0 && SC.hub1 >= 0) {
-            const RegionRec H0 = load_rec(&p.rec[SC.hub0]), H1 = load_rec(&p.rec[SC.hub1]);
-            // two un-finalised hubs may meet through this sub-cluster (a big-big decision) unless their ids forbid it
-            both_open = !H0.fin && !H1.fin && !(H0.con >= 0 && H1.con >= 0 && H0.con != H1.con);
-            same_id = H0.con >= 0 && H0.con == H1.con;
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int h = q ? SC.hub1 : SC.hub0;
-            const bool v = valid && h >= 0;
-            const unsigned act = __ballot_sync(0xffffffffu, v);
-            if (!v) continue;
-            const unsigned peers = __match_any_sync(act, h);
-            const RegionRec H = load_rec(&p.rec[h]);
-            const float d = raw_dist(H, R);
-            const int rmax = __reduce_max_sync(peers, __float_as_int(d));
-            const int mass = __reduce_add_sync(peers, R.sz);
-            NodeScratch* hs = &p.hull[h];
-            if (lane == (unsigned)(__ffs(peers) - 1)) {
-              atomicMax(&hs->rbits, rmax);
-              atomicAdd(&hs->mass, mass);
-            }
-            const int hflags = *((volatile int*)&hs->flags);
-            if ((both_open || (SC.flags & kScHubs3)) && !(hflags & kScUnc)) atomicOr(&hs->flags, kScUnc);   // a dynamic big-big test is possible
-            if ((same_id || ((SC.flags & kScHubs3) && H.con >= 0)) && !(hflags & kScUncAny)) atomicOr(&hs->flags, kScUncAny);
-            if (SC.flags & kScConMulti) { if (!(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti); }
-            else if (SC.con != kNoCon) {
-              int old = *((volatile int*)&hs->con);
-              if (old == kNoCon) old = atomicCAS(&hs->con, kNoCon, SC.con);
-              if (old != kNoCon && old != SC.con && !(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti);
+          if (hub >= 0 && sub >= 0) {
+            NodeScratch* sc = &p.hull[sub];
+            int old = *((volatile int*)&sc->hub0);
+            if (old == -1) old = atomicCAS(&sc->hub0, -1, hub);
+            if (old != -1 && old != hub) {
+              old = *((volatile int*)&sc->hub1);
+              if (old == -1) old = atomicCAS(&sc->hub1, -1, hub);
+              if (old != -1 && old != hub) atomicOr(&sc->flags, kScHubs3);
             }
           }
         }
-      }
-      bar.sync();
-      // ---- C4: count the edges the certificates do not cover ----
-      {
-        unsigned long long mine = 0;
-        for (unsigned long long i = tid; i < n_live; i += nthr) {
-          const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-          const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
-          bool cert = false;
-          if (sa < mins || sb < mins) {
+        bar.sync();
+        // ---- C3: what every hub may absorb in this segment (once per atom and hub) ----
+        for (unsigned long long i0 = tid - lane; i0 < n_master; i0 += nthr) {
+          const unsigned long long i = i0 + lane;
+          bool in = i < n_master;
+          uint4 e = make_uint4(kDone, 0u, 0u, 0u);
+          if (in) { e = reinterpret_cast<const uint4*>(master)[i]; in = VSB_IN_SEG(e); }
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            bool valid = false;
+            RegionRec R;
+            R.sz = 0; R.con = -1; R.d0 = R.d1 = R.d2 = 0.f; R.fin = 0; R.pad0 = R.pad1 = 0;
+            NodeScratch SC;
+            SC.hub0 = SC.hub1 = -1; SC.flags = 0; SC.con = kNoCon;
+            if (in) {
+              const int r = s2 ? (int)e.z : (int)e.y;
+              R = load_rec(&p.rec[r]);
+              if (R.sz >= mins) {
+                // hub side of a hub-small edge: a sub-cluster with more than two hubs makes all of them uncertain
+                const int o = s2 ? (int)e.y : (int)e.z;
+                if (p.rec[o].sz < mins) {
+                  const int c = cl_find(p.cl, o);
+                  if ((p.hull[c].flags & kScHubs3) && (p.hull[r].flags & (kScUnc | kScUncAny)) != (kScUnc | kScUncAny))
+                    atomicOr(&p.hull[r].flags, R.con >= 0 ? (kScUnc | kScUncAny) : kScUnc);
+                }
+              } else if (atomicExch(&p.hull[r].claim, tag_b) != tag_b) {
+                SC = load_sc(&p.hull[cl_find(p.cl, r)]);
+                valid = true;
+              }
+            }
+            bool both_open = false, same_id = false;
+            if (valid && SC.hub0 >= 0 && SC.hub1 >= 0) {
+              const RegionRec H0 = load_rec(&p.rec[SC.hub0]), H1 = load_rec(&p.rec[SC.hub1]);
+              // two un-finalised hubs may meet through this sub-cluster (a big-big decision) unless their ids forbid it
+              both_open = !H0.fin && !H1.fin && !(H0.con >= 0 && H1.con >= 0 && H0.con != H1.con);
+              same_id = H0.con >= 0 && H0.con == H1.con;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int h = q ? SC.hub1 : SC.hub0;
+              const bool v = valid && h >= 0;
+              const unsigned act = __ballot_sync(0xffffffffu, v);
+              if (!v) continue;
+              const unsigned peers = __match_any_sync(act, h);
+              const RegionRec H = load_rec(&p.rec[h]);
+              const float d = raw_dist(H, R);
+              const int rmax = __reduce_max_sync(peers, __float_as_int(d));
+              const int mass = __reduce_add_sync(peers, R.sz);
+              NodeScratch* hs = &p.hull[h];
+              if (lane == (unsigned)(__ffs(peers) - 1)) {
+                atomicMax(&hs->rbits, rmax);
+                atomicAdd(&hs->mass, mass);
+              }
+              const int hflags = *((volatile int*)&hs->flags);
+              if ((both_open || (SC.flags & kScHubs3)) && !(hflags & kScUnc)) atomicOr(&hs->flags, kScUnc);   // a dynamic big-big test is possible
+              if ((same_id || ((SC.flags & kScHubs3) && H.con >= 0)) && !(hflags & kScUncAny)) atomicOr(&hs->flags, kScUncAny);
+              if (SC.flags & kScConMulti) { if (!(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti); }
+              else if (SC.con != kNoCon) {
+                int old = *((volatile int*)&hs->con);
+                if (old == kNoCon) old = atomicCAS(&hs->con, kNoCon, SC.con);
+                if (old != kNoCon && old != SC.con && !(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti);
+              }
+            }
+          }
+        }
+        bar.sync();
+        // ---- C4: count the edges the certificates do not cover ----
+        {
+          unsigned long long mine = 0;
+          for (unsigned long long i = tid; i < n_master; i += nthr) {
+            const uint4 e = reinterpret_cast<const uint4*>(master)[i];
+            if (!VSB_IN_SEG(e)) continue;
+            const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
+            bool cert = false;
+            if (sa < mins || sb < mins) {
+              const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
+              int target;
+              cert = subcluster_certified(p, c, load_sc(&p.hull[c]), wt, mins, &target);
+            }
+            if (!cert) ++mine;
+          }
+          if (mine) atomicAdd(&p.counters[5], mine);
+        }
+        bar.sync();
+        const unsigned long long n_unc = *((volatile unsigned long long*)&p.counters[5]);
+        const bool split = (n_unc > kResidualSplit && seg_hi - seg_lo > kWindowMin);
+        // ---- C5: apply the certified merges (skipped when the segment is halved) ----
+        if (!split) {
+          for (unsigned long long i = tid; i < n_master; i += nthr) {
+            const uint4 e = reinterpret_cast<const uint4*>(master)[i];
+            if (!VSB_IN_SEG(e)) continue;
+            const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;    // sizes are not folded before the next barrier
+            if (sa >= mins && sb >= mins) continue;
             const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
             int target;
-            cert = subcluster_certified(p, c, load_sc(&p.hull[c]), wt, mins, &target);
-          }
-          if (!cert) ++mine;
-        }
-        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&p.counters[5], mine);
-      }
-      bar.sync();
-      const unsigned long long n_unc = *((volatile unsigned long long*)&p.counters[5]);
-      const bool split = (n_unc > kResidualSplit && n_edges > kWindowMin);
-      // ---- C5: apply the certified merges (or only reset the scratch when the window is halved) ----
-      for (unsigned long long i = tid; i < n_live; i += nthr) {
-        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-        if (split) continue;
-        const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;    // sizes are not folded before the next barrier
-        if (sa >= mins && sb >= mins) continue;
-        const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
-        int target;
-        const NodeScratch SC = load_sc(&p.hull[c]);
-        if (!subcluster_certified(p, c, SC, wt, mins, &target)) {
-          // the ordered rounds may let frozen hubs absorb: publish the certificate
+            const NodeScratch SC = load_sc(&p.hull[c]);
+            if (!subcluster_certified(p, c, SC, wt, mins, &target)) {
+              // the ordered rounds may let frozen hubs absorb: publish the certificate
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int h = q ? SC.hub1 : SC.hub0;
-            if (h < 0) continue;
-            if (p.hull[h].frozen != wtag && hub_frozen_eval(load_rec(&p.rec[h]), load_sc(&p.hull[h]), wt)) p.hull[h].frozen = wtag;
-          }
-          continue;
-        }
+              for (int q = 0; q < 2; ++q) {
+                const int h = q ? SC.hub1 : SC.hub0;
+                if (h < 0) continue;
+                if (p.hull[h].frozen != wtag && hub_frozen_eval(load_rec(&p.rec[h]), load_sc(&p.hull[h]), wt)) p.hull[h].frozen = wtag;
+              }
+              continue;
+            }
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int r = s ? (int)e.z : (int)e.y;
-          if (r == target) continue;
-          const int old = atomicExch(&p.parent[r], target);
-          if (old == r) {
-            const RegionRec R = load_rec(&p.rec[r]);
-            if (R.con >= 0) atomicMax(&p.rec[target].con, R.con);
-            acc_add(p.acc, target, R);
-          }
-        }
-        reinterpret_cast<uint4*>(dst)[i].x = kDone;
-        p.done[e.w] = 1;
-      }
-      bar.sync();
-      // ---- C6: fold the bulk contributions, scratch back to idle ----
-      for (unsigned long long i = tid; i < n_live; i += nthr) {
-        const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int r = s ? (int)e.z : (int)e.y;
-          acc_fold(p, r);
-          p.cl[r] = r;
-          reset_sc(&p.hull[r]);
-        }
-      }
-      if (tid == 0) atomicAdd(&p.stats[5], 1ull);
-      if (!split) { if (tid == 0) { atomicAdd(&p.stats[6], n_unc); } break; }
-      n_edges = (n_edges + 1) / 2;
-      raw = n_edges;
-      ++epoch;
-      bar.sync();
-    }
-    const unsigned long long live_setup = n_live;
-    // ---------------- ordered rounds on what is left of the window ----------------
-    if (n_live != 0) {
-      // the certified merges changed roots: every round starts with a fresh prune / reserve pass;
-      // the first one reads the set-up's list (buffer A) and writes buffer B
-      unsigned buf = 1;
-      unsigned long long n_src = n_live, prev_live = ~0ull >> 1;
-      if (tid == 0) p.counters[1] = 0ull;
-      ++epoch;
-      bar.sync();
-      while (true) {
-        if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
-        const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - epoch)) << 32;
-        dst = buf ? p.live_b : p.live_a;
-        const uint32_t* src = buf ? p.live_a : p.live_b;
-        unsigned long long* dst_cnt = &p.counters[buf];
-        // ---- P1: find roots, drop inert edges, reserve ----
-        for (unsigned long long i = tid; i < n_src; i += nthr) {
-          const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
-          const uint32_t code = e0.x, pos = e0.w;
-          if (code == kDone || p.done[pos]) continue;
-          int u, v;
-          decode_edge(p, code, u, v);
-          const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-          bool drop = (ru == rv);
-          if (!drop) {
-            const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-            const bool both_con = (A.con >= 0 && B.con >= 0);
-            drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
-          }
-          if (drop) { p.done[pos] = 1; continue; }
-          const unsigned long long slot = warp_slot(dst_cnt);
-          if (slot < p.live_cap) {
-            reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
-            atomicMin(&p.res[ru], key_hi | code);
-            atomicMin(&p.res[rv], key_hi | code);
+            for (int s2 = 0; s2 < 2; ++s2) {
+              const int r = s2 ? (int)e.z : (int)e.y;
+              if (r == target) continue;
+              const int old = atomicExch(&p.parent[r], target);
+              if (old == r) {
+                const RegionRec R = load_rec(&p.rec[r]);
+                if (R.con >= 0) atomicMax(&p.rec[target].con, R.con);
+                acc_add(p.acc, target, R);
+              }
+            }
+            p.done[e.w] = 2;                      // certified (2 = merged in this pass: scratch reset below still sees it)
           }
         }
         bar.sync();
-        n_live = *((volatile unsigned long long*)dst_cnt);
-        if (n_live > p.live_cap) n_live = p.live_cap;
-        if (n_live == 0) break;
-        if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
-        // ---- chain regime: block 0 finishes (or advances) the window in serial window mode ----
-        if (prev_live - n_live < kSerialSwitch) {
-          if (kIsGrid) {
-            if (blockIdx.x == 0) {
-              const bool fin = serial_rounds(p, S, b, codes, n_edges, wtag);
+        // ---- C6: fold the bulk contributions, scratch back to idle ----
+        for (unsigned long long i = tid; i < n_master; i += nthr) {
+          const uint4 e = reinterpret_cast<const uint4*>(master)[i];
+          if (!(e.w >= seg_lo && e.w < seg_hi)) continue;
+          const unsigned char dn = p.done[e.w];
+          if (dn == 1) continue;                  // was not part of this attempt
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int r = s2 ? (int)e.z : (int)e.y;
+            acc_fold(p, r);
+            p.cl[r] = r;
+            reset_sc(&p.hull[r]);
+          }
+          if (dn == 2) p.done[e.w] = 1;
+        }
+        if (tid == 0) { atomicAdd(&p.stats[5], 1ull); if (!split) atomicAdd(&p.stats[6], n_unc); }
+        bar.sync();
+        if (!split) break;
+        seg_hi = seg_lo + (seg_hi - seg_lo + 1) / 2;
+        seg_len = seg_hi - seg_lo;
+      }
+#undef VSB_IN_SEG
+      // ---------------- ordered rounds on what is left of the segment ----------------
+      if (have_live) {
+        unsigned buf = 0;                        // ordered lists ping-pong between live_b (0) and live_c (1)
+        bool from_master = true;
+        unsigned long long n_src = n_master, prev_live = ~0ull >> 1;
+        if (tid == 0) { p.counters[0] = 0ull; p.counters[1] = 0ull; }
+        ++epoch;
+        bar.sync();
+        while (true) {
+          if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
+          const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - epoch)) << 32;
+          uint32_t* dst = buf ? p.live_c : p.live_b;
+          const uint32_t* src = from_master ? master : (buf ? p.live_b : p.live_c);
+          unsigned long long* dst_cnt = &p.counters[buf];
+          // ---- P1: find roots, drop inert edges, reserve ----
+          for (unsigned long long i = tid; i < n_src; i += nthr) {
+            const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
+            const uint32_t code = e0.x, pos = e0.w;
+            if (from_master && !(pos >= seg_lo && pos < seg_hi)) continue;
+            if (p.done[pos]) continue;
+            int u, v;
+            decode_edge(p, code, u, v);
+            const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+            bool drop = (ru == rv);
+            if (!drop) {
+              const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+              const bool both_con = (A.con >= 0 && B.con >= 0);
+              drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+            }
+            if (drop) { p.done[pos] = 1; continue; }
+            const unsigned long long slot = warp_slot(dst_cnt);
+            if (slot < p.live_cap) {
+              reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
+              atomicMin(&p.res[ru], key_hi | code);
+              atomicMin(&p.res[rv], key_hi | code);
+            }
+          }
+          bar.sync();
+          unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
+          if (n_live > p.live_cap) n_live = p.live_cap;
+          if (n_live == 0) break;
+          if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
+          // ---- chain regime: block 0 finishes (or advances) the segment in serial window mode ----
+          if (prev_live - n_live < kSerialSwitch) {
+            if (kIsGrid) {
+              if (blockIdx.x == 0) {
+                const bool fin = serial_rounds(p, S, b, codes + seg_lo, seg_hi - seg_lo, wtag, p.done + seg_lo);
+                if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+              }
+            } else {
+              const bool fin = serial_rounds(p, S, b, codes + seg_lo, seg_hi - seg_lo, wtag, p.done + seg_lo);
               if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
             }
-          } else {
-            const bool fin = serial_rounds(p, S, b, codes, n_edges, wtag);
-            if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
+            bar.sync();
+            const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
+            if (finished) break;
+            // productive again: the next grid round re-reads this round's list (done flags filter it)
+            if (tid == 0) p.counters[buf ^ 1] = 0ull;
+            bar.sync();
+            n_src = n_live;
+            from_master = false;
+            prev_live = ~0ull >> 1;       // force at least one grid round
+            buf ^= 1;
+            ++epoch;
+            continue;
+          }
+          prev_live = n_live;
+          // ---- P3: commit (strict owners + absorption by frozen hubs) ----
+          for (unsigned long long i = tid; i < n_live; i += nthr) {
+            const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+            const int ru = (int)e.y, rv = (int)e.z;
+            const unsigned long long key = key_hi | e.x;
+            const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
+            bool done = false;
+            if (own_u && own_v) {
+              exec_strict(p, ru, rv, edge_w, p.stats);
+              done = true;
+            } else if (own_u || own_v) {
+              const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+              // the edge is the next edge of the side it owns; the other side is a hub whose
+              // decision-relevant state cannot change in this segment
+              if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
+                p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true;
+              } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
+                p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true;
+              }
+            }
+            if (done) p.done[e.w] = 1;
           }
           bar.sync();
-          const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
-          if (finished) break;
-          // productive again: the next grid round re-reads this round's list (done flags filter it)
-          if (tid == 0) p.counters[buf ^ 1] = 0ull;
+          // ---- P4: fold bulk contributions ----
+          for (unsigned long long i = tid; i < n_live; i += nthr) {
+            const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+            acc_fold(p, (int)e.y);
+            acc_fold(p, (int)e.z);
+          }
+          if (tid == 0) {
+            p.counters[buf ^ 1] = 0ull;          // the other buffer becomes the next destination
+            atomicAdd(&p.stats[0], 1ull);
+          }
           bar.sync();
           n_src = n_live;
-          prev_live = ~0ull >> 1;       // force at least one grid round
+          from_master = false;
           buf ^= 1;
           ++epoch;
-          continue;
         }
-        prev_live = n_live;
-        // ---- P3: commit (strict owners + absorption by frozen hubs) ----
-        for (unsigned long long i = tid; i < n_live; i += nthr) {
-          const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-          const int ru = (int)e.y, rv = (int)e.z;
-          const unsigned long long key = key_hi | e.x;
-          const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
-          bool done = false;
-          if (own_u && own_v) {
-            exec_strict(p, ru, rv, edge_w, p.stats);
-            done = true;
-          } else if (own_u || own_v) {
-            const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-            // the edge is the next edge of the side it owns; the other side is a hub whose
-            // decision-relevant state cannot change in this window
-            if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
-              p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true;
-            } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
-              p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true;
-            }
-          }
-          if (done) {
-            reinterpret_cast<uint4*>(dst)[i].x = kDone;
-            p.done[e.w] = 1;
-          }
-        }
-        bar.sync();
-        // ---- P4: fold bulk contributions ----
-        for (unsigned long long i = tid; i < n_live; i += nthr) {
-          const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-          acc_fold(p, (int)e.y);
-          acc_fold(p, (int)e.z);
-        }
-        if (tid == 0) {
-          p.counters[buf ^ 1] = 0ull;          // the other buffer becomes the next destination
-          atomicAdd(&p.stats[0], 1ull);
-        }
-        bar.sync();
-        n_src = n_live;
-        buf ^= 1;
-        ++epoch;
       }
+      // ---- the hub-hub edge that ended the segment runs alone, exactly (a real big-big decision) ----
+      const bool at_hubhub = (seg_hi == hh && hh < n_edges);
+      if (at_hubhub && tid == 0) {
+        int u, v;
+        decode_edge(p, codes[hh], u, v);
+        const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+        if (ru != rv) exec_strict(p, ru, rv, edge_w, p.stats);
+        p.done[hh] = 1;
+      }
+      seg_lo = at_hubhub ? hh + 1 : seg_hi;
+      if (seg_lo >= n_edges) break;
+      if (seg_hi == seg_end) seg_len = min(seg_len * 2, n_edges);     // the whole planned segment went through: grow again
+      // ---- refresh: roots of the entries still ahead, drop what became inert, next hub-hub edge ----
+      if (tid == 0) p.counters[4] = ~0ull;
+      ++epoch;
+      bar.sync();
+      for (unsigned long long i = tid; i < n_master; i += nthr) {
+        uint4 e = reinterpret_cast<const uint4*>(master)[i];
+        if (e.w < seg_lo || p.done[e.w]) continue;
+        const int ru = uf_find(p.parent, (int)e.y), rv = uf_find(p.parent, (int)e.z);
+        bool drop = (ru == rv);
+        bool hubhub = false;
+        if (!drop) {
+          const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+          const bool both_con = (A.con >= 0 && B.con >= 0);
+          drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+          hubhub = !drop && A.sz >= mins && B.sz >= mins;
+        }
+        if (drop) { p.done[e.w] = 1; continue; }
+        if (hubhub) atomicMin(&p.counters[4], (unsigned long long)e.w);
+        if (ru != (int)e.y || rv != (int)e.z) { e.y = (uint32_t)ru; e.z = (uint32_t)rv; reinterpret_cast<uint4*>(master)[i] = e; }
+      }
+      bar.sync();
+      hh = *((volatile unsigned long long*)&p.counters[4]);
     }
     // next window: aim at kWindowTarget live edges
     w0 += n_edges;
     {
-      const unsigned long long live0 = live_setup ? live_setup : 1;
+      const unsigned long long live0 = n_master ? n_master : 1;
       unsigned long long next = raw;
-      if (n_edges >= raw) {   // the window was not cut short: adapt to the live density
-        if (live0 * 2 < kWindowTarget) next = raw * 2;
-        if (live0 * 8 < kWindowTarget) next = raw * 4;
-        if (live0 > kWindowTarget * 2) next = raw / 2;
-      }
+      if (live0 * 2 < kWindowTarget) next = raw * 2;
+      if (live0 * 8 < kWindowTarget) next = raw * 4;
+      if (live0 > kWindowTarget * 2) next = raw / 2;
       raw = max(next, kWindowMin);
     }
     ++epoch;
