@@ -160,13 +160,13 @@ int vsb200_dense::init() {
   ENG_CUDA(cudaMalloc(&mp.acc, nodes * 32));
   ENG_CUDA(cudaMalloc(&mp.cl, nodes * 4));
   ENG_CUDA(cudaMalloc(&mp.hull, nodes * sizeof(NodeScratch)));
-  ENG_CUDA(cudaMalloc(&mp.counters, 16 * 8));
+  ENG_CUDA(cudaMalloc(&mp.counters, (16 + 2048) * 8));   // + per-block counts of the ordered compaction
   mp.stats = mp.counters + 8;
   mp.debug = nullptr;
   mp.trace = nullptr;
   ENG_CUDA(cudaMemsetAsync(mp.res, 0xff, nodes * 8, stream));
   ENG_CUDA(cudaMemsetAsync(mp.acc, 0, nodes * 32, stream));
-  ENG_CUDA(cudaMemsetAsync(mp.counters, 0, 16 * 8, stream));
+  ENG_CUDA(cudaMemsetAsync(mp.counters, 0, (16 + 2048) * 8, stream));
   ENG_RC(launch_init_iota(mp.cl, (long long)nodes, stream));
   ENG_RC(launch_init_hull(mp.hull, (long long)nodes, stream));
   ENG_CUDA(cudaMalloc(&d_labels, nodes * sizeof(int)));

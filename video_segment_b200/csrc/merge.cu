@@ -318,8 +318,9 @@ __device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsig
 
 // Returns true when the bucket is finished, false when the window became productive again
 // (many commits per round: hand back to the grid-wide rounds).
+// pend[0 .. n_edges) = positions (relative to codes / done_flags) of the segment's pending edges in reference order
 __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b, const uint32_t* codes,
-                              const unsigned long long n_edges, const int wtag, unsigned char* done_flags) {
+                              const uint32_t* pend_list, const unsigned long long n_edges, const int wtag, unsigned char* done_flags) {
   const float inv_scale = (float)(1.0 / (double)bucket_scale());
   const float edge_w = (float)b * inv_scale;
   const int mins = p.min_region_size;
@@ -338,16 +339,18 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
       const int wn = S.wn;
       const unsigned long long cur = S.cursor;
       if (wn >= kWin || cur >= n_edges) break;
-      const unsigned long long pos = cur + tid;
-      const bool pend = (pos < n_edges) && (done_flags[pos] == 0);
+      const unsigned long long idx = cur + tid;
+      uint32_t pos = 0;
+      bool pend = false;
+      if (idx < n_edges) { pos = pend_list[idx]; pend = (done_flags[pos] == 0); }
       unsigned total;
       const unsigned rank = block_rank(S, pend, &total);
       const unsigned room = (unsigned)(kWin - wn);
       if (tid == 0) S.next_cursor = cur + kMergeThreads;
       __syncthreads();
       if (pend) {
-        if (rank < room) { S.code[wn + rank] = codes[pos]; S.pos[wn + rank] = (uint32_t)pos; }
-        else if (rank == room) S.next_cursor = pos;      // first pending edge that did not fit
+        if (rank < room) { S.code[wn + rank] = codes[pos]; S.pos[wn + rank] = pos; }
+        else if (rank == room) S.next_cursor = idx;      // first pending edge that did not fit
       }
       __syncthreads();
       if (tid == 0) { S.wn = wn + (int)min(total, room); S.cursor = S.next_cursor; S.commits = 0; }
@@ -1225,13 +1228,47 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
           // ---- chain regime: block 0 finishes (or advances) the segment in serial window mode ----
           if (prev_live - n_live < kSerialSwitch) {
+            // ordered list of the segment's pending positions (stable compaction of the done flags by the
+            // whole grid: every block takes a contiguous slice), written to the list buffer not in use
+            uint32_t* pend_list = buf ? p.live_b : p.live_c;
+            const unsigned nblk = kIsGrid ? gridDim.x : 1u, blk = kIsGrid ? blockIdx.x : 0u;
+            const unsigned long long range = seg_hi - seg_lo;
+            const unsigned long long slice = (range + nblk - 1) / nblk;
+            const unsigned long long s_lo = min(range, (unsigned long long)blk * slice), s_hi = min(range, s_lo + slice);
+            const unsigned char* dflags = p.done + seg_lo;
+            unsigned long long* blockcnt = p.counters + 16;
+            {
+              unsigned cnt = 0;
+              for (unsigned long long i = s_lo + threadIdx.x; i < s_hi; i += blockDim.x) cnt += (dflags[i] == 0) ? 1u : 0u;
+              for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+              if ((threadIdx.x & 31) == 0) S.warp_cnt[threadIdx.x >> 5] = cnt;
+              __syncthreads();
+              if (threadIdx.x == 0) {
+                unsigned long long t = 0;
+                for (int k = 0; k < kMergeWarps; ++k) t += S.warp_cnt[k];
+                blockcnt[blk] = t;
+              }
+              __syncthreads();
+            }
+            bar.sync();
+            unsigned long long offset = 0, n_pend = 0;
+            for (unsigned k = 0; k < nblk; ++k) { const unsigned long long c = *((volatile unsigned long long*)&blockcnt[k]); if (k < blk) offset += c; n_pend += c; }
+            for (unsigned long long base = s_lo; base < s_hi; base += blockDim.x) {
+              const unsigned long long i = base + threadIdx.x;
+              const bool flag = (i < s_hi) && (dflags[i] == 0);
+              unsigned total;
+              const unsigned rank = block_rank(S, flag, &total);
+              if (flag) pend_list[offset + rank] = (uint32_t)i;
+              offset += total;
+            }
+            bar.sync();
             if (kIsGrid) {
               if (blockIdx.x == 0) {
-                const bool fin = serial_rounds(p, S, b, codes + seg_lo, seg_hi - seg_lo, wtag, p.done + seg_lo);
+                const bool fin = serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
                 if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
               }
             } else {
-              const bool fin = serial_rounds(p, S, b, codes + seg_lo, seg_hi - seg_lo, wtag, p.done + seg_lo);
+              const bool fin = serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
               if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
             }
             bar.sync();
