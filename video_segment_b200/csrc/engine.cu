@@ -5,7 +5,9 @@
 // arrays.  Every per-pixel / per-edge step is a CUDA kernel launch (preprocess.cu, edges.cu,
 // sort.cu, merge.cu, results.cu); the host only keeps O(#regions + #scan intervals) bookkeeping.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -92,6 +94,7 @@ struct vsb200_dense {
   double h2d_bytes = 0, d2h_bytes = 0, edge_ms = 0, edge_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> edge_events;   // timing of the edge-build launches
   int time_edges = 0;
+  int host_threads = 1;          // worker threads of the O(#scan intervals) host shaping
 
   ~vsb200_dense() { release(); }
   void release();
@@ -504,6 +507,9 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
                 dbg[b * 4 + 1] - prev_r, dbg[b * 4 + 0] / 1000.0);
         prev_r = dbg[b * 4 + 1]; prev_w = dbg[b * 4 + 3];
       }
+      const unsigned long long* c = &dbg[kNumBuckets * 4 + 8];
+      fprintf(f, "uncertified edge-attempts: hubhub %llu con %llu hubs3 %llu hubless_fin %llu hubless_diam %llu race %llu hub_not_frozen %llu bigmass %llu\n",
+              c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
       fclose(f);
     }
   }
@@ -590,8 +596,22 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     if (use_flow) for (int s = 0; s < slots; ++s) flows.push_back(h_flows[s].empty() ? nullptr : h_flows[s].data());
     int next_label = (int)nodes;
     const int num_regions = (int)regions.size();
+    // the per-region tube analysis is independent: host worker threads (the reference runs it serially)
+    std::vector<std::vector<vsbh::Tube>> all_tubes(num_regions);
+    {
+      const int nt = std::max(1, std::min<int>(host_threads, num_regions));
+      std::atomic<int> next_region{0};
+      auto work = [&]() {
+        for (int r = next_region.fetch_add(1); r < num_regions; r = next_region.fetch_add(1))
+          all_tubes[r] = vsbh::split_region_into_tubes(regions[r]->raster, w, h, use_flow ? &flows : nullptr);
+      };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+      work();
+      for (auto& th : pool) th.join();
+    }
     for (int r = 0; r < num_regions; ++r) {
-      std::vector<vsbh::Tube> tubes = vsbh::split_region_into_tubes(regions[r]->raster, w, h, use_flow ? &flows : nullptr);
+      std::vector<vsbh::Tube>& tubes = all_tubes[r];
       if (tubes.empty()) continue;
       int keep = -1, keep_score = 0;
       std::vector<float> areas(tubes.size());
@@ -682,8 +702,9 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   max_region_id = std::max(max_region_id, max_id + 1);
   const int chunk_sz = last_output_frame - curr_chunk_start + 1;
   const int hierarchy_frame_idx = num_output_frames;
-  std::vector<int32_t> idmap_host;
-  for (int f = curr_chunk_start; f <= max_result_frame; ++f) {
+  const int n_out_frames = max_result_frame - curr_chunk_start + 1;
+  std::vector<std::unique_ptr<FrameOut>> frame_outs(std::max(n_out_frames, 0));
+  auto build_frame = [&](int f) {
     // RetrieveSegmentation3D (segmentation.cpp:458-533)
     std::unique_ptr<FrameOut> out(new FrameOut);
     out->width = w; out->height = h; out->chunk_id = chunk_id;
@@ -739,6 +760,19 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
           std::fill(out->id_map.begin() + (size_t)y * w + lx, out->id_map.begin() + (size_t)y * w + rx + 1, out->region_id[k]);
         }
     }
+    frame_outs[f - curr_chunk_start] = std::move(out);
+  };
+  {
+    const int nt = std::max(1, std::min(host_threads, n_out_frames));
+    std::atomic<int> next_frame{curr_chunk_start};
+    auto work = [&]() { for (int f = next_frame.fetch_add(1); f <= max_result_frame; f = next_frame.fetch_add(1)) build_frame(f); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+  }
+  for (int f = curr_chunk_start; f <= max_result_frame; ++f) {
+    std::unique_ptr<FrameOut> out = std::move(frame_outs[f - curr_chunk_start]);
     if (f <= last_output_frame) {
       if (f < last_output_frame) {
         results->push_back(std::move(out));
@@ -860,6 +894,11 @@ int vsb200_dense_create(const vsb200_dense_opts* o, int width, int height, int u
   std::unique_ptr<vsb200_dense> d(new vsb200_dense);
   d->o = *o; d->w = width; d->h = height; d->use_flow = use_flow != 0; d->l1 = (o->color_distance == 0);
   d->overlap_frames = overlap;
+  {
+    const unsigned hc = std::thread::hardware_concurrency();
+    d->host_threads = (int)std::min(16u, std::max(1u, hc));
+    if (const char* e = getenv("VSB200_HOST_THREADS")) d->host_threads = std::max(1, atoi(e));
+  }
   d->constraint_frames = std::min(o->num_constraint_frames, overlap - 1);
   if (int rc = d->init()) return rc;
   *out = d.release();

@@ -866,6 +866,124 @@ __device__ __forceinline__ bool subcluster_certified(const MergeParams& p, int c
   return !H.fin && !(S.flags & kScFin) && diam < t.thr_m;
 }
 
+// debugging tap: why is the sub-cluster not certified (mirrors subcluster_certified)
+__device__ int subcluster_why(const MergeParams& p, const NodeScratch& S, const WindowThr& t, int mins) {
+  if (S.flags & kScConMulti) return 1;
+  if (S.flags & kScHubs3) return 2;
+  const float dx = __int_as_float(S.mx[0]) - __int_as_float(S.mn[0]);
+  const float dy = __int_as_float(S.mx[1]) - __int_as_float(S.mn[1]);
+  const float dz = __int_as_float(S.mx[2]) - __int_as_float(S.mn[2]);
+  const float diam = sqrtf((dx * dx + dy * dy + dz * dz) * (1.0f / 3.0f));
+  if (S.con != kNoCon && !(diam < t.con_thr)) return 1;
+  if (S.hub0 < 0) return (S.flags & kScFin) ? 3 : 4;
+  if (S.hub1 >= 0) return 5;
+  const RegionRec H = load_rec(&p.rec[S.hub0]);
+  if (H.con >= 0 && S.con != kNoCon && S.con != H.con) return 1;
+  if (!hub_frozen_eval(H, load_sc(&p.hull[S.hub0]), t)) return 6;
+  return 7;
+}
+
+constexpr unsigned long long kBlockRoundsLimit = 1024;   // residual lists up to this size are finished by block 0 alone
+
+struct RoundState { unsigned epoch, buf; bool from_master; unsigned long long n_src, prev_live; };
+
+// Ordered rounds on the pending edges of segment [seg_lo, seg_hi): deterministic reservations (the
+// earliest pending edge of both of its roots runs the exact serial decision tree) + absorption by
+// frozen hubs.  Lists ping-pong between live_b (buf 0) and live_c (buf 1); the first round reads the
+// window's master list.  Returns 0 = segment finished, 1 = dependency chain (progress per round below
+// the threshold; the list of the last P1 is in buffer st.buf), 2 = list not larger than small_limit
+// (handed over at a round boundary), 3 = watchdog.
+template <class Bar>
+__device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid, const unsigned nthr, const int b,
+                              const float edge_w, const int wtag, const uint32_t* master, const unsigned long long seg_lo,
+                              const unsigned long long seg_hi, RoundState& st, const unsigned long long small_limit,
+                              const unsigned long long stall_progress, unsigned long long& guard) {
+  const int mins = p.min_region_size;
+  while (true) {
+    if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return 3; }
+    const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - st.epoch)) << 32;
+    uint32_t* dst = st.buf ? p.live_c : p.live_b;
+    const uint32_t* src = st.from_master ? master : (st.buf ? p.live_b : p.live_c);
+    unsigned long long* dst_cnt = &p.counters[st.buf];
+    // ---- P1: find roots, drop inert edges, reserve ----
+    for (unsigned long long i = tid; i < st.n_src; i += nthr) {
+      const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
+      const uint32_t code = e0.x, pos = e0.w;
+      if (st.from_master && !(pos >= seg_lo && pos < seg_hi)) continue;
+      if (p.done[pos]) continue;
+      int u, v;
+      decode_edge(p, code, u, v);
+      const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+      bool drop = (ru == rv);
+      if (!drop) {
+        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+        const bool both_con = (A.con >= 0 && B.con >= 0);
+        drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+      }
+      if (drop) { p.done[pos] = 1; continue; }
+      const unsigned long long slot = warp_slot(dst_cnt);
+      if (slot < p.live_cap) {
+        reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
+        atomicMin(&p.res[ru], key_hi | code);
+        atomicMin(&p.res[rv], key_hi | code);
+      }
+    }
+    bar.sync();
+    unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
+    if (n_live > p.live_cap) n_live = p.live_cap;
+    if (n_live == 0) return 0;
+    if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
+    const unsigned long long need = stall_progress ? stall_progress : max(8ull, n_live >> 6);
+    if (st.prev_live - n_live < need) return 1;                      // chain regime
+    if (small_limit && n_live <= small_limit) {
+      // hand the list over at a round boundary: the next P1 (block 0) re-reads it
+      if (tid == 0) p.counters[st.buf ^ 1] = 0ull;
+      bar.sync();
+      st.n_src = n_live; st.from_master = false; st.prev_live = ~0ull >> 1; st.buf ^= 1; ++st.epoch;
+      return 2;
+    }
+    st.prev_live = n_live;
+    // ---- P3: commit (strict owners + absorption by frozen hubs) ----
+    for (unsigned long long i = tid; i < n_live; i += nthr) {
+      const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+      const int ru = (int)e.y, rv = (int)e.z;
+      const unsigned long long key = key_hi | e.x;
+      const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
+      bool done = false;
+      if (own_u && own_v) {
+        exec_strict(p, ru, rv, edge_w, p.stats);
+        done = true;
+      } else if (own_u || own_v) {
+        const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
+        // the edge is the next edge of the side it owns; the other side is a hub whose
+        // decision-relevant state cannot change in this segment
+        if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
+          p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true;
+        } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
+          p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true;
+        }
+      }
+      if (done) p.done[e.w] = 1;
+    }
+    bar.sync();
+    // ---- P4: fold bulk contributions ----
+    for (unsigned long long i = tid; i < n_live; i += nthr) {
+      const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
+      acc_fold(p, (int)e.y);
+      acc_fold(p, (int)e.z);
+    }
+    if (tid == 0) {
+      p.counters[st.buf ^ 1] = 0ull;          // the other buffer becomes the next destination
+      atomicAdd(&p.stats[0], 1ull);
+    }
+    bar.sync();
+    st.n_src = n_live;
+    st.from_master = false;
+    st.buf ^= 1;
+    ++st.epoch;
+  }
+}
+
 // counters: [0] live count of buffer A, [1] of buffer B, [2] round epoch, [3] serial result flag,
 //           [4] first hub-hub position of the window, [5] uncertified edge count, [6] window tag
 // live entry = 4 words: code, ru, rv, position in the window
@@ -1118,8 +1236,10 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             if (sa < mins || sb < mins) {
               const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
               int target;
-              cert = subcluster_certified(p, c, load_sc(&p.hull[c]), wt, mins, &target);
-            }
+              const NodeScratch SCc = load_sc(&p.hull[c]);
+              cert = subcluster_certified(p, c, SCc, wt, mins, &target);
+              if (!cert && p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8 + subcluster_why(p, SCc, wt, mins)], 1ull);
+            } else if (p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8], 1ull);
             if (!cert) ++mine;
           }
           if (mine) atomicAdd(&p.counters[5], mine);
@@ -1186,143 +1306,65 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
 #undef VSB_IN_SEG
       // ---------------- ordered rounds on what is left of the segment ----------------
       if (have_live) {
-        unsigned buf = 0;                        // ordered lists ping-pong between live_b (0) and live_c (1)
-        bool from_master = true;
-        unsigned long long n_src = n_master, prev_live = ~0ull >> 1;
+        RoundState st;
+        st.epoch = epoch + 1; st.buf = 0; st.from_master = true; st.n_src = n_master; st.prev_live = ~0ull >> 1;
         if (tid == 0) { p.counters[0] = 0ull; p.counters[1] = 0ull; }
-        ++epoch;
         bar.sync();
-        while (true) {
-          if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
-          const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - epoch)) << 32;
-          uint32_t* dst = buf ? p.live_c : p.live_b;
-          const uint32_t* src = from_master ? master : (buf ? p.live_b : p.live_c);
-          unsigned long long* dst_cnt = &p.counters[buf];
-          // ---- P1: find roots, drop inert edges, reserve ----
-          for (unsigned long long i = tid; i < n_src; i += nthr) {
-            const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
-            const uint32_t code = e0.x, pos = e0.w;
-            if (from_master && !(pos >= seg_lo && pos < seg_hi)) continue;
-            if (p.done[pos]) continue;
-            int u, v;
-            decode_edge(p, code, u, v);
-            const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-            bool drop = (ru == rv);
-            if (!drop) {
-              const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-              const bool both_con = (A.con >= 0 && B.con >= 0);
-              drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
-            }
-            if (drop) { p.done[pos] = 1; continue; }
-            const unsigned long long slot = warp_slot(dst_cnt);
-            if (slot < p.live_cap) {
-              reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
-              atomicMin(&p.res[ru], key_hi | code);
-              atomicMin(&p.res[rv], key_hi | code);
-            }
+        // big lists: grid-wide rounds; small lists: block 0 alone behind __syncthreads (a round then costs
+        // a few microseconds instead of three grid barriers); dependency chains: serial window mode
+        int status = ordered_rounds<Bar>(p, bar, tid, nthr, b, edge_w, wtag, master, seg_lo, seg_hi, st,
+                                         kIsGrid ? kBlockRoundsLimit : 0ull, kSerialSwitch, guard);
+        if (kIsGrid && status == 2) {
+          if (blockIdx.x == 0) {
+            BlockBar bb;
+            const int s2 = ordered_rounds<BlockBar>(p, bb, threadIdx.x, blockDim.x, b, edge_w, wtag, master, seg_lo, seg_hi, st,
+                                                    0ull, 0ull, guard);
+            if (threadIdx.x == 0) { p.counters[3] = (unsigned long long)s2; p.counters[8 + 3] = (unsigned long long)st.buf; p.counters[2] = st.epoch; }
           }
           bar.sync();
-          unsigned long long n_live = *((volatile unsigned long long*)dst_cnt);
-          if (n_live > p.live_cap) n_live = p.live_cap;
-          if (n_live == 0) break;
-          if (tid == 0) { trace(p, 0, (unsigned long long)b); trace(p, 1, guard); trace(p, 2, n_live); trace(p, 3, 1); }
-          // ---- chain regime: block 0 finishes (or advances) the segment in serial window mode ----
-          if (prev_live - n_live < kSerialSwitch) {
-            // ordered list of the segment's pending positions (stable compaction of the done flags by the
-            // whole grid: every block takes a contiguous slice), written to the list buffer not in use
-            uint32_t* pend_list = buf ? p.live_b : p.live_c;
-            const unsigned nblk = kIsGrid ? gridDim.x : 1u, blk = kIsGrid ? blockIdx.x : 0u;
-            const unsigned long long range = seg_hi - seg_lo;
-            const unsigned long long slice = (range + nblk - 1) / nblk;
-            const unsigned long long s_lo = min(range, (unsigned long long)blk * slice), s_hi = min(range, s_lo + slice);
-            const unsigned char* dflags = p.done + seg_lo;
-            unsigned long long* blockcnt = p.counters + 16;
-            {
-              unsigned cnt = 0;
-              for (unsigned long long i = s_lo + threadIdx.x; i < s_hi; i += blockDim.x) cnt += (dflags[i] == 0) ? 1u : 0u;
-              for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-              if ((threadIdx.x & 31) == 0) S.warp_cnt[threadIdx.x >> 5] = cnt;
-              __syncthreads();
-              if (threadIdx.x == 0) {
-                unsigned long long t = 0;
-                for (int k = 0; k < kMergeWarps; ++k) t += S.warp_cnt[k];
-                blockcnt[blk] = t;
-              }
-              __syncthreads();
+          status = (int)*((volatile unsigned long long*)&p.counters[3]);
+          st.buf = (unsigned)*((volatile unsigned long long*)&p.counters[8 + 3]);
+          st.epoch = (unsigned)*((volatile unsigned long long*)&p.counters[2]);
+        }
+        epoch = st.epoch;
+        if (status == 3) return;                 // watchdog
+        if (status == 1) {
+          // ordered list of the segment's pending positions (stable compaction of the done flags by the
+          // whole grid: every block takes a contiguous slice), written to the list buffer not in use
+          uint32_t* pend_list = st.buf ? p.live_b : p.live_c;
+          const unsigned nblk = kIsGrid ? gridDim.x : 1u, blk = kIsGrid ? blockIdx.x : 0u;
+          const unsigned long long range = seg_hi - seg_lo;
+          const unsigned long long slice = (range + nblk - 1) / nblk;
+          const unsigned long long s_lo = min(range, (unsigned long long)blk * slice), s_hi = min(range, s_lo + slice);
+          const unsigned char* dflags = p.done + seg_lo;
+          unsigned long long* blockcnt = p.counters + 16;
+          {
+            unsigned cnt = 0;
+            for (unsigned long long i = s_lo + threadIdx.x; i < s_hi; i += blockDim.x) cnt += (dflags[i] == 0) ? 1u : 0u;
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if ((threadIdx.x & 31) == 0) S.warp_cnt[threadIdx.x >> 5] = cnt;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+              unsigned long long t = 0;
+              for (int k = 0; k < kMergeWarps; ++k) t += S.warp_cnt[k];
+              blockcnt[blk] = t;
             }
-            bar.sync();
-            unsigned long long offset = 0, n_pend = 0;
-            for (unsigned k = 0; k < nblk; ++k) { const unsigned long long c = *((volatile unsigned long long*)&blockcnt[k]); if (k < blk) offset += c; n_pend += c; }
-            for (unsigned long long base = s_lo; base < s_hi; base += blockDim.x) {
-              const unsigned long long i = base + threadIdx.x;
-              const bool flag = (i < s_hi) && (dflags[i] == 0);
-              unsigned total;
-              const unsigned rank = block_rank(S, flag, &total);
-              if (flag) pend_list[offset + rank] = (uint32_t)i;
-              offset += total;
-            }
-            bar.sync();
-            if (kIsGrid) {
-              if (blockIdx.x == 0) {
-                const bool fin = serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
-                if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
-              }
-            } else {
-              const bool fin = serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
-              if (threadIdx.x == 0) p.counters[3] = fin ? 1ull : 0ull;
-            }
-            bar.sync();
-            const bool finished = *((volatile unsigned long long*)&p.counters[3]) != 0ull;
-            if (finished) break;
-            // productive again: the next grid round re-reads this round's list (done flags filter it)
-            if (tid == 0) p.counters[buf ^ 1] = 0ull;
-            bar.sync();
-            n_src = n_live;
-            from_master = false;
-            prev_live = ~0ull >> 1;       // force at least one grid round
-            buf ^= 1;
-            ++epoch;
-            continue;
-          }
-          prev_live = n_live;
-          // ---- P3: commit (strict owners + absorption by frozen hubs) ----
-          for (unsigned long long i = tid; i < n_live; i += nthr) {
-            const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-            const int ru = (int)e.y, rv = (int)e.z;
-            const unsigned long long key = key_hi | e.x;
-            const bool own_u = (p.res[ru] == key), own_v = (p.res[rv] == key);
-            bool done = false;
-            if (own_u && own_v) {
-              exec_strict(p, ru, rv, edge_w, p.stats);
-              done = true;
-            } else if (own_u || own_v) {
-              const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-              // the edge is the next edge of the side it owns; the other side is a hub whose
-              // decision-relevant state cannot change in this segment
-              if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
-                p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true;
-              } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
-                p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true;
-              }
-            }
-            if (done) p.done[e.w] = 1;
+            __syncthreads();
           }
           bar.sync();
-          // ---- P4: fold bulk contributions ----
-          for (unsigned long long i = tid; i < n_live; i += nthr) {
-            const uint4 e = reinterpret_cast<const uint4*>(dst)[i];
-            acc_fold(p, (int)e.y);
-            acc_fold(p, (int)e.z);
-          }
-          if (tid == 0) {
-            p.counters[buf ^ 1] = 0ull;          // the other buffer becomes the next destination
-            atomicAdd(&p.stats[0], 1ull);
+          unsigned long long offset = 0, n_pend = 0;
+          for (unsigned k = 0; k < nblk; ++k) { const unsigned long long c = *((volatile unsigned long long*)&blockcnt[k]); if (k < blk) offset += c; n_pend += c; }
+          for (unsigned long long base = s_lo; base < s_hi; base += blockDim.x) {
+            const unsigned long long i = base + threadIdx.x;
+            const bool flag = (i < s_hi) && (dflags[i] == 0);
+            unsigned total;
+            const unsigned rank = block_rank(S, flag, &total);
+            if (flag) pend_list[offset + rank] = (uint32_t)i;
+            offset += total;
           }
           bar.sync();
-          n_src = n_live;
-          from_master = false;
-          buf ^= 1;
-          ++epoch;
+          if (!kIsGrid || blockIdx.x == 0) serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
+          bar.sync();
         }
       }
       // ---- the hub-hub edge that ended the segment runs alone, exactly (a real big-big decision) ----

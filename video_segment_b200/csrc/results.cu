@@ -298,13 +298,64 @@ __global__ void neighbor_pairs_kernel(const int* __restrict__ roots, const int* 
   }
 }
 
+// No-flow variant: one thread per voxel, one grid row per image row (32-bit index arithmetic, the
+// 13 neighbour loads of a warp fall into 5 cache lines).
+__global__ void __launch_bounds__(256) neighbor_pairs_rows_kernel(const int* __restrict__ roots, const int* __restrict__ labels,
+                                                                  int w, int h, int virtual_slot0,
+                                                                  unsigned long long* __restrict__ table, unsigned cap_mask,
+                                                                  unsigned long long* __restrict__ out,
+                                                                  unsigned long long* __restrict__ out_count,
+                                                                  unsigned long long out_cap) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;                     // slot * h + y
+  if (x >= w) return;
+  const int slot = row / h, y = row - slot * h;
+  const size_t base = (size_t)row * w;
+  const int* r0 = roots + base;
+  const int* l0 = labels + base;
+  const int ra = __ldg(&r0[x]);
+  int la = -1, last = -2;
+#define VSB_PAIR2(RP, LP, XX)                                                               \
+  { const int rb = __ldg(&(RP)[XX]);                                                        \
+    if (rb != ra) { if (la == -1) la = __ldg(&l0[x]); const int lb = __ldg(&(LP)[XX]);      \
+      if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } } }
+  if (!(virtual_slot0 && slot == 0)) {
+    if (x + 1 < w) VSB_PAIR2(r0, l0, x + 1)
+    if (y + 1 < h) {
+      const int* r1 = r0 + w; const int* l1 = l0 + w;
+      VSB_PAIR2(r1, l1, x)
+      if (x > 0) VSB_PAIR2(r1, l1, x - 1)
+      if (x + 1 < w) VSB_PAIR2(r1, l1, x + 1)
+    }
+  }
+  if (slot > 0) {
+    const size_t pbase = base - (size_t)h * w;    // same pixel, previous slot
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      const int* rp = roots + pbase + (ptrdiff_t)dy * w;
+      const int* lp = labels + pbase + (ptrdiff_t)dy * w;
+      if (x > 0) VSB_PAIR2(rp, lp, x - 1)
+      VSB_PAIR2(rp, lp, x)
+      if (x + 1 < w) VSB_PAIR2(rp, lp, x + 1)
+    }
+  }
+#undef VSB_PAIR2
+}
+
 int launch_neighbor_pairs(const int* roots, const int* labels, int w, int h, int slots, const float* flows, int virtual_slot0,
                           unsigned long long* table, unsigned table_cap_pow2, unsigned long long* out,
                           unsigned long long* out_count, unsigned long long out_cap, cudaStream_t s) {
   VSB_CUDA_OK(cudaMemsetAsync(table, 0xff, sizeof(unsigned long long) * (size_t)table_cap_pow2, s));
   VSB_CUDA_OK(cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), s));
-  neighbor_pairs_kernel<<<148 * 8, 256, 0, s>>>(roots, labels, w, h, slots, flows, virtual_slot0, table, table_cap_pow2 - 1,
-                                               out, out_count, out_cap);
+  if (!flows && (long long)slots * h <= 65535) {
+    dim3 grid((w + 255) / 256, slots * h);
+    neighbor_pairs_rows_kernel<<<grid, 256, 0, s>>>(roots, labels, w, h, virtual_slot0, table, table_cap_pow2 - 1, out, out_count, out_cap);
+  } else {
+    neighbor_pairs_kernel<<<148 * 8, 256, 0, s>>>(roots, labels, w, h, slots, flows, virtual_slot0, table, table_cap_pow2 - 1,
+                                                 out, out_count, out_cap);
+  }
   VSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
