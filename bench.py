@@ -162,9 +162,10 @@ def main():
     K, W = args.steps, args.warmup
     if W < 3:
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
+    from video_segment_b200.shard import group_range
     frames_per_rank = 1 + FRAMES_PER_STEP * (W + K)
     # One video, sharded: rank g owns frames [g * L, (g + 1) * L] (one read-overlap frame).
-    start = rank * (frames_per_rank - 1)
+    start, _ = group_range(rank, world, frames_per_rank)
     host_frames = list(synth(3, w, h, min(UNIQUE_FRAMES, frames_per_rank), start=start))
     dev_frames = [torch.from_numpy(f).cuda() for f in host_frames]
     pinned = [torch.from_numpy(f).pin_memory() for f in host_frames]
@@ -178,20 +179,12 @@ def main():
     halo_in = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
 
     def seam_exchange(unit):
-        """C1: overlap id maps to the successor group; C2: all-gather of the region-id counts."""
+        """C1: overlap id maps to the successor group; C2: all-gather of the region-id counts (shard.py)."""
         if world == 1:
             return
+        from video_segment_b200.shard import seam_exchange as _seam
         max_id = unit.export_halo(halo[0].data_ptr(), halo[1].data_ptr())
-        ops = []
-        if rank + 1 < world:
-            ops.append(dist.P2POp(dist.isend, halo, rank + 1))
-        if rank > 0:
-            ops.append(dist.P2POp(dist.irecv, halo_in, rank - 1))
-        reqs = dist.batch_isend_irecv(ops) if ops else []
-        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([max_id], dtype=torch.int64, device="cuda"))
-        for r in reqs:
-            r.wait()
+        _seam(halo, halo_in, max_id, rank, world)
 
     def run_leg(device_resident):
         unit = DenseSegmentationUnit(device=local_rank)

@@ -1001,6 +1001,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
   int wtag = (int)(*((volatile unsigned long long*)&p.counters[6]));
   bar.sync();                                   // everybody has read the persistent counters
   unsigned long long w0 = 0;
+  unsigned long long target = kWindowTarget;   // live edges aimed at per window: grows while windows certify cleanly
   unsigned long long raw = min(bucket_edges, kWindowTarget);
   unsigned long long guard = 0;
   uint32_t* const master = p.live_a;            // live list of the window (code, ru, rv, position)
@@ -1074,6 +1075,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     unsigned long long hh = *((volatile unsigned long long*)&p.counters[4]);   // first live edge between two hubs
     // ---------------- segments of the window: [seg_lo, seg_hi) in window positions ----------------
     unsigned long long seg_lo = 0, seg_len = n_edges;
+    bool any_split = false;
+    unsigned long long unc_sum = 0;
     while (n_master != 0 && seg_lo < n_edges) {
       if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
       const unsigned long long seg_end = min(min(hh, n_edges), seg_lo + seg_len);   // a hub-hub edge ends the segment in front of it
@@ -1189,12 +1192,29 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
                 valid = true;
               }
             }
-            bool both_open = false, same_id = false;
-            if (valid && SC.hub0 >= 0 && SC.hub1 >= 0) {
+            // Two hubs sharing a sub-cluster may meet inside the segment (a dynamic big-big decision).  If
+            // the rules forbid or neutralise the meeting (different constraint ids; one side finalised and not
+            // both carrying one id) nothing happens.  Otherwise each hub counts the other as something it may
+            // absorb: the frozen bound then also certifies that their meeting ends in a merge.  Done once per
+            // sub-cluster, by the lane that claimed the sub-cluster's root atom.
+            bool pair_unc_any = false;
+            if (valid && SC.hub0 >= 0 && SC.hub1 >= 0 && !(SC.flags & kScHubs3) && cl_find(p.cl, s2 ? (int)e.z : (int)e.y) == (s2 ? (int)e.z : (int)e.y)) {
               const RegionRec H0 = load_rec(&p.rec[SC.hub0]), H1 = load_rec(&p.rec[SC.hub1]);
-              // two un-finalised hubs may meet through this sub-cluster (a big-big decision) unless their ids forbid it
-              both_open = !H0.fin && !H1.fin && !(H0.con >= 0 && H1.con >= 0 && H0.con != H1.con);
-              same_id = H0.con >= 0 && H0.con == H1.con;
+              const bool both_con = H0.con >= 0 && H1.con >= 0;
+              bool contribute = false;
+              if (both_con) {
+                if (H0.con == H1.con) { if (H0.fin != H1.fin) pair_unc_any = true; else contribute = true; }
+              } else if (!H0.fin && !H1.fin) contribute = true;
+              if (contribute) {
+                const int dbits = __float_as_int(raw_dist(H0, H1));
+                NodeScratch* h0 = &p.hull[SC.hub0];
+                NodeScratch* h1 = &p.hull[SC.hub1];
+                atomicMax(&h0->rbits, dbits); atomicAdd(&h0->mass, H1.sz);
+                atomicMax(&h1->rbits, dbits); atomicAdd(&h1->mass, H0.sz);
+                if (H0.con < 0 && H1.con >= 0) { const int old = atomicCAS(&h0->con, kNoCon, H1.con); if (old != kNoCon && old != H1.con) atomicOr(&h0->flags, kScConMulti); }
+                if (H1.con < 0 && H0.con >= 0) { const int old = atomicCAS(&h1->con, kNoCon, H0.con); if (old != kNoCon && old != H0.con) atomicOr(&h1->flags, kScConMulti); }
+              }
+              if (pair_unc_any) { atomicOr(&p.hull[SC.hub0].flags, kScUncAny); atomicOr(&p.hull[SC.hub1].flags, kScUncAny); }
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -1213,8 +1233,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
                 atomicAdd(&hs->mass, mass);
               }
               const int hflags = *((volatile int*)&hs->flags);
-              if ((both_open || (SC.flags & kScHubs3)) && !(hflags & kScUnc)) atomicOr(&hs->flags, kScUnc);   // a dynamic big-big test is possible
-              if ((same_id || ((SC.flags & kScHubs3) && H.con >= 0)) && !(hflags & kScUncAny)) atomicOr(&hs->flags, kScUncAny);
+              if ((SC.flags & kScHubs3) && !(hflags & kScUnc)) atomicOr(&hs->flags, kScUnc);   // more than two hubs: not analysed
+              if (((SC.flags & kScHubs3) && H.con >= 0) && !(hflags & kScUncAny)) atomicOr(&hs->flags, kScUncAny);
               if (SC.flags & kScConMulti) { if (!(hflags & kScConMulti)) atomicOr(&hs->flags, kScConMulti); }
               else if (SC.con != kNoCon) {
                 int old = *((volatile int*)&hs->con);
@@ -1299,7 +1319,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         }
         if (tid == 0) { atomicAdd(&p.stats[5], 1ull); if (!split) atomicAdd(&p.stats[6], n_unc); }
         bar.sync();
-        if (!split) break;
+        if (!split) { unc_sum += n_unc; break; }
+        any_split = true;
         seg_hi = seg_lo + (seg_hi - seg_lo + 1) / 2;
         seg_len = seg_hi - seg_lo;
       }
@@ -1405,11 +1426,13 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     // next window: aim at kWindowTarget live edges
     w0 += n_edges;
     {
+      if (any_split) target = max(target / 2, kWindowTarget / 4);
+      else if (unc_sum * 64 <= n_master) target = min(target * 2, kWindowTarget * 32);
       const unsigned long long live0 = n_master ? n_master : 1;
       unsigned long long next = raw;
-      if (live0 * 2 < kWindowTarget) next = raw * 2;
-      if (live0 * 8 < kWindowTarget) next = raw * 4;
-      if (live0 > kWindowTarget * 2) next = raw / 2;
+      if (live0 * 2 < target) next = raw * 2;
+      if (live0 * 8 < target) next = raw * 4;
+      if (live0 > target * 2) next = raw / 2;
       raw = max(next, kWindowMin);
     }
     ++epoch;
