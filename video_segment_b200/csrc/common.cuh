@@ -65,7 +65,7 @@ struct __align__(32) RegionRec {
 
 // Per-node scratch of the window certification stage (merge.cu).  A small root uses its slot as the
 // record of the sub-cluster it represents, a big root ("hub") as its absorption bound.  Idle state
-// between windows: mn = 0x7f7f7f7f, mx = 0, flags = 0, con = kNoCon, mass = 0, hubs = -1, rbits = 0, num = 0.
+// between windows: mn = 0x7f7f7f7f, mx = 0, flags = 0, con = kNoCon, mass = 0, hubs = -1, rbits = 0.
 struct __align__(16) NodeScratch {
   int mn[3];                 // colour hull of the members (float bits; colours are >= 0)
   int mx[3];
@@ -74,7 +74,7 @@ struct __align__(16) NodeScratch {
   int mass;                  // voxels of the members / of the atoms a hub may absorb
   int hub0, hub1;            // big roots adjacent to the sub-cluster (-1 = none)
   int rbits;                 // hub: max distance to an absorbable atom (float bits)
-  unsigned long long num;    // spare
+  unsigned long long num;    // ordered rounds: earliest pending edge to another big region (epoch tagged, never reset)
   int claim;                 // window tag of the last once-per-atom claim (never reset)
   int frozen;                // window tag in which this hub's decision-relevant state is certified constant
 };

@@ -687,8 +687,9 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
         const RegionRec& B = Bs[q];
         bool done = false;
         // the other side is a hub whose decision-relevant state cannot change in this window (see run_bucket)
-        if (k == 2 && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        else if (k == 3 && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+        // (records were loaded before this round's runs: a hub merged away by a run is skipped until the next round)
+        if (k == 2 && B.con < 0 && A.sz >= mins && p.parent[ru] == ru && p.parent[rv] == rv && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
+        else if (k == 3 && A.con < 0 && B.sz >= mins && p.parent[ru] == ru && p.parent[rv] == rv && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         if (done) {
           done_flags[S.pos[i]] = 1;
           S.code[i] = kDone;
@@ -819,7 +820,7 @@ __device__ __forceinline__ void reset_sc(NodeScratch* s) {
   q[0] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
   q[1] = make_int4(0, 0, 0, kNoCon);
   q[2] = make_int4(0, -1, -1, 0);
-  s->num = 0ull;                     // claim / frozen tags stay
+  // num (epoch-tagged big-big key), claim / frozen tags stay
 }
 
 struct WindowThr { float thr_m, con_thr; };
@@ -834,10 +835,10 @@ __device__ __forceinline__ bool hub_frozen_eval(const RegionRec& H, const NodeSc
     if (S.flags & kScConMulti) return false;
     if (S.con != kNoCon) conset = S.con;
   }
+  (void)conset;      // the 0.15 split test against same-id pieces is checked per sub-cluster (subcluster_certified)
   const float R = __int_as_float(S.rbits);
   const double M = (double)S.mass, Sz = (double)H.sz;
   const float delta = (float)((double)R * M / (Sz + M)) * 1.0001f + 1e-7f;   // drift of the hub mean, see above
-  if (conset >= 0 && !(R + delta < t.con_thr)) return false;
   if (!H.fin) {
     if (S.flags & kScUnc) return false;
     if (!(R + delta < t.thr_m)) return false;
@@ -861,6 +862,22 @@ __device__ __forceinline__ bool subcluster_certified(const MergeParams& p, int c
   const NodeScratch HS = load_sc(&p.hull[S.hub0]);
   if (H.con >= 0 && S.con != kNoCon && S.con != H.con) return false;      // foreign id: those edges are kept, the rest races
   if (!hub_frozen_eval(H, HS, t)) return false;
+  if (S.con != kNoCon) {
+    // constrained pieces meeting a hub that carries (or will have taken) the same id are merged only
+    // while the colour distance stays <= 0.15 (segmentation_graph.h:417-437): bound it by the farthest
+    // corner of the sub-cluster's hull plus the hub's drift
+    float s2 = 0.f;
+    const float hm[3] = {H.d0, H.d1, H.d2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float dd = fmaxf(fabsf(__int_as_float(S.mx[k]) - hm[k]), fabsf(__int_as_float(S.mn[k]) - hm[k]));
+      s2 += dd * dd;
+    }
+    const float far = sqrtf(s2 * (1.0f / 3.0f));
+    const float Rh = __int_as_float(HS.rbits);
+    const float delta = (float)((double)Rh * (double)HS.mass / ((double)H.sz + (double)HS.mass)) * 1.0001f + 1e-7f;
+    if (!(far + delta < t.con_thr)) return false;
+  }
   *target = S.hub0;
   if (S.mass < mins) return true;
   return !H.fin && !(S.flags & kScFin) && diam < t.thr_m;
@@ -915,12 +932,20 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
       decode_edge(p, code, u, v);
       const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
       bool drop = (ru == rv);
+      bool bigbig = false;
       if (!drop) {
         const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
         const bool both_con = (A.con >= 0 && B.con >= 0);
         drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+        bigbig = !drop && A.sz >= mins && B.sz >= mins;
       }
       if (drop) { p.done[pos] = 1; continue; }
+      if (bigbig) {
+        // a pending edge between two big regions: absorptions into either of them that come later in
+        // reference order wait for it (it may merge the hub away in the round it executes)
+        atomicMin(&p.hull[ru].num, key_hi | code);
+        atomicMin(&p.hull[rv].num, key_hi | code);
+      }
       const unsigned long long slot = warp_slot(dst_cnt);
       if (slot < p.live_cap) {
         reinterpret_cast<uint4*>(dst)[slot] = make_uint4(code, (uint32_t)ru, (uint32_t)rv, pos);
@@ -956,11 +981,14 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
       } else if (own_u || own_v) {
         const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
         // the edge is the next edge of the side it owns; the other side is a hub whose
-        // decision-relevant state cannot change in this segment
+        // decision-relevant state cannot change in this segment (and that no earlier big-big edge can
+        // merge away in this round)
         if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
-          p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true;
+          const unsigned long long bb = p.hull[ru].num;
+          if (!((bb >> 32) == (key_hi >> 32) && (uint32_t)bb < e.x)) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
         } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
-          p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true;
+          const unsigned long long bb = p.hull[rv].num;
+          if (!((bb >> 32) == (key_hi >> 32) && (uint32_t)bb < e.x)) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         }
       }
       if (done) p.done[e.w] = 1;

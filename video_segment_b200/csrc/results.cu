@@ -413,7 +413,7 @@ __global__ void init_hull_kernel(NodeScratch* sc, long long n) {
     q[0] = make_int4(0x7f7f7f7f, 0x7f7f7f7f, 0x7f7f7f7f, 0);
     q[1] = make_int4(0, 0, 0, kNoCon);
     q[2] = make_int4(0, -1, -1, 0);
-    q[3] = make_int4(0, 0, 0, 0);
+    q[3] = make_int4(-1, -1, 0, 0);       // num = ~0 (epoch-tagged big-big key, see merge.cu), claim, frozen
   }
 }
 int launch_init_hull(NodeScratch* hull, long long n_nodes, cudaStream_t s) {
