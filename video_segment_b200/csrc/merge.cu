@@ -22,6 +22,7 @@
 // One persistent cooperative launch walks all 2048 buckets; buckets with few pending edges
 // are finished by block 0 alone behind __syncthreads instead of grid-wide barriers.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -1233,6 +1234,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
               if (both_con) {
                 if (H0.con == H1.con) { if (H0.fin != H1.fin) pair_unc_any = true; else contribute = true; }
               } else if (!H0.fin && !H1.fin) contribute = true;
+              if (contribute && (p.dev_flags & 1)) { contribute = false; pair_unc_any = true; atomicOr(&p.hull[SC.hub0].flags, kScUnc); atomicOr(&p.hull[SC.hub1].flags, kScUnc); }
               if (contribute) {
                 const int dbits = __float_as_int(raw_dist(H0, H1));
                 NodeScratch* h0 = &p.hull[SC.hub0];
@@ -1362,7 +1364,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         // big lists: grid-wide rounds; small lists: block 0 alone behind __syncthreads (a round then costs
         // a few microseconds instead of three grid barriers); dependency chains: serial window mode
         int status = ordered_rounds<Bar>(p, bar, tid, nthr, b, edge_w, wtag, master, seg_lo, seg_hi, st,
-                                         kIsGrid ? kBlockRoundsLimit : 0ull, kSerialSwitch, guard);
+                                         (kIsGrid && !(p.dev_flags & 4)) ? kBlockRoundsLimit : 0ull, kSerialSwitch, guard);
         if (kIsGrid && status == 2) {
           if (blockIdx.x == 0) {
             BlockBar bb;
@@ -1455,7 +1457,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     w0 += n_edges;
     {
       if (any_split) target = max(target / 2, kWindowTarget / 4);
-      else if (unc_sum * 64 <= n_master) target = min(target * 2, kWindowTarget * 32);
+      else if (unc_sum * 64 <= n_master && !(p.dev_flags & 2)) target = min(target * 2, kWindowTarget * 32);
       const unsigned long long live0 = n_master ? n_master : 1;
       unsigned long long next = raw;
       if (live0 * 2 < target) next = raw * 2;
@@ -1552,7 +1554,9 @@ int launch_init_virtual_nodes(const int* constraint_ids, int slot, int w, int h,
   return 0;
 }
 
-int launch_merge(const MergeParams& p, cudaStream_t s) {
+int launch_merge(const MergeParams& p_in, cudaStream_t s) {
+  MergeParams p = p_in;
+  p.dev_flags = getenv("VSB200_MERGE_FLAGS") ? atoi(getenv("VSB200_MERGE_FLAGS")) : 0;
   int dev = 0, sms = 0, per_sm = 0;
   VSB_CUDA_OK(cudaGetDevice(&dev));
   VSB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
