@@ -72,6 +72,20 @@ def test_single_chunk_matches_oracle_exactly(real_clip):
     assert st["kernel_launches"] > 0
 
 
+def test_region_sizes_equal_voxel_counts():
+    """Self-consistency at a size the oracle is not needed for: the region sizes of the hierarchy (device
+    union-find records after bulk / ordered merges) equal the voxel counts of the id maps."""
+    clip = synth_clip(3, 640, 480, 14)
+    got, _, _ = _run_gpu(clip)
+    ids = np.stack([g["id_map"] for g in got])
+    uid, cnt = np.unique(ids, return_counts=True)
+    true = dict(zip(uid.tolist(), cnt.tolist()))
+    comp = got[0]["compound"]
+    assert len(comp) == len(uid)
+    bad = [(int(r[0]), int(r[1]), true.get(int(r[0]))) for r in comp if true.get(int(r[0])) != int(r[1])]
+    assert not bad, bad[:8]
+
+
 def test_streaming_chunks_match_oracle(real_clip):
     clip = np.concatenate([real_clip, real_clip[::-1]])          # 48 frames -> 3 chunks
     got, batches, st = _run_gpu(clip)

@@ -689,8 +689,8 @@ __device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b
         bool done = false;
         // the other side is a hub whose decision-relevant state cannot change in this window (see run_bucket)
         // (records were loaded before this round's runs: a hub merged away by a run is skipped until the next round)
-        if (k == 2 && B.con < 0 && A.sz >= mins && p.parent[ru] == ru && p.parent[rv] == rv && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        else if (k == 3 && A.con < 0 && B.sz >= mins && p.parent[ru] == ru && p.parent[rv] == rv && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
+        if (k == 2 && B.con < 0 && A.sz >= mins && B.sz < mins && p.parent[ru] == ru && p.parent[rv] == rv && (A.fin || p.hull[ru].frozen == wtag)) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
+        else if (k == 3 && A.con < 0 && B.sz >= mins && A.sz < mins && p.parent[ru] == ru && p.parent[rv] == rv && (B.fin || p.hull[rv].frozen == wtag)) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         if (done) {
           done_flags[S.pos[i]] = 1;
           S.code[i] = kDone;
@@ -981,13 +981,14 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
         done = true;
       } else if (own_u || own_v) {
         const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
-        // the edge is the next edge of the side it owns; the other side is a hub whose
+        // the edge is the next edge of the SMALL side it owns; the other side is a hub whose
         // decision-relevant state cannot change in this segment (and that no earlier big-big edge can
-        // merge away in this round)
-        if (own_v && B.con < 0 && A.sz >= mins && ((A.fin && B.sz < mins) || (!A.fin && p.hull[ru].frozen == wtag))) {
+        // merge away in this round).  Only small regions are absorbed this way: a big one may itself be
+        // collecting absorptions in this round, which would be lost with it.
+        if (own_v && B.con < 0 && A.sz >= mins && B.sz < mins && (A.fin || p.hull[ru].frozen == wtag)) {
           const unsigned long long bb = p.hull[ru].num;
           if (!((bb >> 32) == (key_hi >> 32) && (uint32_t)bb < e.x)) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        } else if (own_u && A.con < 0 && B.sz >= mins && ((B.fin && A.sz < mins) || (!B.fin && p.hull[rv].frozen == wtag))) {
+        } else if (own_u && A.con < 0 && B.sz >= mins && A.sz < mins && (B.fin || p.hull[rv].frozen == wtag)) {
           const unsigned long long bb = p.hull[rv].num;
           if (!((bb >> 32) == (key_hi >> 32) && (uint32_t)bb < e.x)) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         }
