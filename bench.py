@@ -262,7 +262,7 @@ def main():
                 "h2d_bytes_per_step": leg_e2e["io"]["h2d_bytes"] / K, "d2h_bytes_per_step": leg_e2e["io"]["d2h_bytes"] / K},
         "gpu_launches": int(leg_dev["stats"]["kernel_launches"]),
         "clocks": leg_dev["clocks"],
-        "roofline": {"bound": "hbm", "kernel": "edge_build_tiled_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "edge_build_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": edge_build_bytes(w, h), "ms_per_launch": edge_ms, "launches_timed": int(io["edge_launches"])},
         "stage_ms_per_step": {k2: v / K for k2, v in leg_dev["stats"].items() if k2.endswith("_ms")},
