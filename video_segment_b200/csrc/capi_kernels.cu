@@ -160,8 +160,8 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.live_cap = max_bucket;
     mp.counters = (unsigned long long*)dalloc((16 + 2048) * 8);
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
-    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 16) * 8) : nullptr;
-    if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 16) * 8, s);
+    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 32) * 8) : nullptr;
+    if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, s);
     mp.trace = nullptr;
     unsigned long long* h_trace = nullptr;
     std::atomic<bool> trace_stop{false};
@@ -202,7 +202,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
       break;
     }
     if (mp.debug) {
-      std::vector<unsigned long long> dbg(kNumBuckets * 4 + 16);
+      std::vector<unsigned long long> dbg(kNumBuckets * 4 + 32);
       cudaMemcpy(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost);
       FILE* f = fopen(getenv("VSB200_MERGE_DEBUG"), "w");
       if (f) {

@@ -491,11 +491,11 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   mp.live_cap = live_cap_alloc;
   ENG_CUDA(cudaMemsetAsync(mp.stats, 0, 8 * 8, stream));
   const char* dbg_path = getenv("VSB200_MERGE_DEBUG");       // per-bucket profile of every chunk (development tap)
-  if (dbg_path && !mp.debug) ENG_CUDA(cudaMalloc(&mp.debug, (kNumBuckets * 4 + 16) * 8));
-  if (mp.debug) ENG_CUDA(cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 16) * 8, stream));
+  if (dbg_path && !mp.debug) ENG_CUDA(cudaMalloc(&mp.debug, (kNumBuckets * 4 + 32) * 8));
+  if (mp.debug) ENG_CUDA(cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, stream));
   ENG_RC(launch_merge(mp, stream));
   if (mp.debug && dbg_path) {
-    std::vector<unsigned long long> dbg(kNumBuckets * 4 + 16);
+    std::vector<unsigned long long> dbg(kNumBuckets * 4 + 32);
     ENG_CUDA(cudaMemcpyAsync(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost, stream));
     ENG_CUDA(cudaStreamSynchronize(stream));
     const std::string path = std::string(dbg_path) + ".chunk" + std::to_string(chunk_id);
@@ -510,6 +510,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
       const unsigned long long* c = &dbg[kNumBuckets * 4 + 8];
       fprintf(f, "uncertified edge-attempts: hubhub %llu con %llu hubs3 %llu hubless_fin %llu hubless_diam %llu race %llu hub_not_frozen %llu bigmass %llu\n",
               c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+      fprintf(f, "hub_not_frozen reasons: same_id_or_hubs3 %llu con_conflict %llu open_hubs3 %llu bound %llu\n", c[8], c[9], c[10], c[11]);
       fclose(f);
     }
   }

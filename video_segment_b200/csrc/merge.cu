@@ -897,7 +897,13 @@ __device__ int subcluster_why(const MergeParams& p, const NodeScratch& S, const 
   if (S.hub1 >= 0) return 5;
   const RegionRec H = load_rec(&p.rec[S.hub0]);
   if (H.con >= 0 && S.con != kNoCon && S.con != H.con) return 1;
-  if (!hub_frozen_eval(H, load_sc(&p.hull[S.hub0]), t)) return 6;
+  const NodeScratch HS = load_sc(&p.hull[S.hub0]);
+  if (!hub_frozen_eval(H, HS, t)) {
+    // finer reason: +16 same-id / >2 hubs, +17 constraint ids conflict, +18 may meet an open hub (>2 hubs), +19 bound
+    const int why = (HS.flags & kScUncAny) ? 16 : (H.con < 0 && (HS.flags & kScConMulti)) ? 17 : (!H.fin && (HS.flags & kScUnc)) ? 18 : 19;
+    atomicAdd(&p.debug[kNumBuckets * 4 + why], 1ull);
+    return 6;
+  }
   return 7;
 }
 
@@ -927,11 +933,11 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
     for (unsigned long long i = tid; i < st.n_src; i += nthr) {
       const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
       const uint32_t code = e0.x, pos = e0.w;
-      if (st.from_master && !(pos >= seg_lo && pos < seg_hi)) continue;
-      if (p.done[pos]) continue;
-      int u, v;
-      decode_edge(p, code, u, v);
-      const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+      if (st.from_master) {
+        if (!(pos >= seg_lo && pos < seg_hi) || p.done[pos]) continue;
+      } else if (code == kDone) continue;          // executed in the previous round's commit
+      // the entry carries the roots of an earlier pass: climbing from them is shorter than from the voxels
+      const int ru = uf_find(p.parent, (int)e0.y), rv = uf_find(p.parent, (int)e0.z);
       bool drop = (ru == rv);
       bool bigbig = false;
       if (!drop) {
@@ -993,7 +999,7 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
           if (!((bb >> 32) == (key_hi >> 32) && (uint32_t)bb < e.x)) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
         }
       }
-      if (done) p.done[e.w] = 1;
+      if (done) { p.done[e.w] = 1; reinterpret_cast<uint4*>(dst)[i].x = kDone; }
     }
     bar.sync();
     // ---- P4: fold bulk contributions ----
