@@ -909,6 +909,114 @@ __device__ int subcluster_why(const MergeParams& p, const NodeScratch& S, const 
 
 constexpr unsigned long long kBlockRoundsLimit = 1024;   // residual lists up to this size are finished by block 0 alone
 
+// ---------------------------------------------------------------------------------------------
+// Exact scan.  A small residual (<= kScanMax pending edges of one segment, in reference order) is
+// finished by one CTA the way the reference does it: all threads stage the edges' current roots and
+// their records in shared memory (compact local ids through a shared hash), ONE thread then walks the
+// edges in order with a local union-find and the exact decision tree, and all threads write the
+// result back.  Cost ~ 0.1 us per edge, independent of the dependency depth (an ordered round costs
+// three grid barriers plus several dependent global loads, and a chain needs one round per link).
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanMax = 1024;
+struct ScanShared {
+  unsigned short ea[kScanMax], eb[kScanMax];       // local ids of an edge's two roots
+  uint32_t epos[kScanMax];
+  int tru[kScanMax], trv[kScanMax];                 // global roots of an edge (staging)
+  int gid[2 * kScanMax];                            // local id -> global root
+  unsigned short par[2 * kScanMax];                 // local union-find
+  int sz[2 * kScanMax], con[2 * kScanMax], fin[2 * kScanMax];
+  float d0[2 * kScanMax], d1[2 * kScanMax], d2[2 * kScanMax];
+  unsigned hkey[4 * kScanMax];                      // hash: global root + 1 (0 = empty)
+  unsigned short hidx[4 * kScanMax];                // local id of the slot's root
+  int n_roots;
+};
+static_assert(sizeof(ScanShared) <= sizeof(SerialShared), "ScanShared overlays SerialShared");
+
+// phase 1 (insert) and phase 2 (lookup, after a block barrier) of the root -> local id hash
+__device__ __forceinline__ void scan_insert(ScanShared& C, unsigned root) {
+  unsigned slot = (root * 2654435761u) >> 20;       // 12 bits
+  while (true) {
+    const unsigned k = atomicCAS(&C.hkey[slot], 0u, root + 1u);
+    if (k == 0u) {
+      const int id = atomicAdd(&C.n_roots, 1);
+      C.gid[id] = (int)root;
+      C.hidx[slot] = (unsigned short)id;
+      return;
+    }
+    if (k == root + 1u) return;
+    slot = (slot + 1u) & (4 * kScanMax - 1);
+  }
+}
+__device__ __forceinline__ unsigned short scan_lookup(const ScanShared& C, unsigned root) {
+  unsigned slot = (root * 2654435761u) >> 20;
+  while (C.hkey[slot] != root + 1u) slot = (slot + 1u) & (4 * kScanMax - 1);
+  return C.hidx[slot];
+}
+
+// all threads of ONE block; pend_list[0 .. n_pend) ascending positions relative to codes / done_flags
+__device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, const uint32_t* codes, const uint32_t* pend_list,
+                           const int n_pend, unsigned char* done_flags) {
+  const float edge_w = (float)b * (float)(1.0 / (double)bucket_scale());
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < 4 * kScanMax; i += nthr) { C.hkey[i] = 0u; C.hidx[i] = 0xFFFFu; }
+  if (tid == 0) C.n_roots = 0;
+  __syncthreads();
+  for (int i = tid; i < n_pend; i += nthr) {
+    const uint32_t pos = pend_list[i];
+    int u, v;
+    decode_edge(p, codes[pos], u, v);
+    const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+    C.epos[i] = pos;
+    C.tru[i] = ru; C.trv[i] = rv;
+    scan_insert(C, (unsigned)ru);
+    scan_insert(C, (unsigned)rv);
+  }
+  __syncthreads();
+  for (int i = tid; i < n_pend; i += nthr) {
+    C.ea[i] = scan_lookup(C, (unsigned)C.tru[i]);
+    C.eb[i] = scan_lookup(C, (unsigned)C.trv[i]);
+  }
+  __syncthreads();
+  const int n_roots = C.n_roots;
+  for (int j = tid; j < n_roots; j += nthr) {
+    const RegionRec R = load_rec(&p.rec[C.gid[j]]);
+    C.par[j] = (unsigned short)j;
+    C.sz[j] = R.sz; C.con[j] = R.con; C.fin[j] = R.fin; C.d0[j] = R.d0; C.d1[j] = R.d1; C.d2[j] = R.d2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    auto findl = [&](int x) { int q = C.par[x]; while (q != x) { const int g = C.par[q]; C.par[x] = (unsigned short)g; x = q; q = g; } return x; };
+    for (int i = 0; i < n_pend; ++i) {
+      const int a = findl(C.ea[i]), bq = findl(C.eb[i]);
+      if (a == bq) continue;
+      RegionRec A, B;
+      A.sz = C.sz[a]; A.con = C.con[a]; A.fin = C.fin[a]; A.d0 = C.d0[a]; A.d1 = C.d1[a]; A.d2 = C.d2[a]; A.pad0 = A.pad1 = 0;
+      B.sz = C.sz[bq]; B.con = C.con[bq]; B.fin = C.fin[bq]; B.d0 = C.d0[bq]; B.d1 = C.d1[bq]; B.d2 = C.d2[bq]; B.pad0 = B.pad1 = 0;
+      const int r = decide_pair(p, A, B, edge_w);      // rep_1 = root of region_1 (the anchor), as in the reference
+      C.sz[a] = A.sz; C.con[a] = A.con; C.fin[a] = A.fin; C.d0[a] = A.d0; C.d1[a] = A.d1; C.d2[a] = A.d2;
+      C.sz[bq] = B.sz; C.con[bq] = B.con; C.fin[bq] = B.fin; C.d0[bq] = B.d0; C.d1[bq] = B.d1; C.d2[bq] = B.d2;
+      if (r == 1) C.par[bq] = (unsigned short)a;
+      else if (r == 2) C.par[a] = (unsigned short)bq;
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < n_roots; j += nthr) {
+    int x = j;
+    while (C.par[x] != x) x = C.par[x];
+    const int g = C.gid[j];
+    if (x == j) {
+      RegionRec R;
+      R.sz = C.sz[j]; R.con = C.con[j]; R.fin = C.fin[j]; R.d0 = C.d0[j]; R.d1 = C.d1[j]; R.d2 = C.d2[j]; R.pad0 = R.pad1 = 0;
+      store_rec(&p.rec[g], R);
+    } else {
+      p.parent[g] = C.gid[x];
+    }
+  }
+  for (int i = tid; i < n_pend; i += nthr) done_flags[C.epos[i]] = 1;
+  if (tid == 0) atomicAdd(&p.stats[3], 1ull);
+  __syncthreads();
+}
+
 struct RoundState { unsigned epoch, buf; bool from_master; unsigned long long n_src, prev_live; };
 
 // Ordered rounds on the pending edges of segment [seg_lo, seg_hi): deterministic reservations (the
@@ -924,7 +1032,7 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
                               const unsigned long long stall_progress, unsigned long long& guard) {
   const int mins = p.min_region_size;
   while (true) {
-    if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return 3; }
+    if (++guard > (1ull << 22)) { if (tid == 0) { printf("vsb200 merge: round watchdog bucket %d\n", b); p.stats[7] = 1ull; } return 3; }
     const unsigned long long key_hi = ((unsigned long long)(0xFFFFFFFFu - st.epoch)) << 32;
     uint32_t* dst = st.buf ? p.live_c : p.live_b;
     const uint32_t* src = st.from_master ? master : (st.buf ? p.live_b : p.live_c);
@@ -1114,7 +1222,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
     bool any_split = false;
     unsigned long long unc_sum = 0;
     while (n_master != 0 && seg_lo < n_edges) {
-      if (++guard > (1ull << 24)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
+      if (++guard > (1ull << 22)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
       const unsigned long long seg_end = min(min(hh, n_edges), seg_lo + seg_len);   // a hub-hub edge ends the segment in front of it
       unsigned long long seg_hi = seg_end;
       bool have_live = false;
@@ -1372,21 +1480,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         // a few microseconds instead of three grid barriers); dependency chains: serial window mode
         int status = ordered_rounds<Bar>(p, bar, tid, nthr, b, edge_w, wtag, master, seg_lo, seg_hi, st,
                                          (kIsGrid && !(p.dev_flags & 4)) ? kBlockRoundsLimit : 0ull, kSerialSwitch, guard);
-        if (kIsGrid && status == 2) {
-          if (blockIdx.x == 0) {
-            BlockBar bb;
-            const int s2 = ordered_rounds<BlockBar>(p, bb, threadIdx.x, blockDim.x, b, edge_w, wtag, master, seg_lo, seg_hi, st,
-                                                    0ull, 0ull, guard);
-            if (threadIdx.x == 0) { p.counters[3] = (unsigned long long)s2; p.counters[8 + 3] = (unsigned long long)st.buf; p.counters[2] = st.epoch; }
-          }
-          bar.sync();
-          status = (int)*((volatile unsigned long long*)&p.counters[3]);
-          st.buf = (unsigned)*((volatile unsigned long long*)&p.counters[8 + 3]);
-          st.epoch = (unsigned)*((volatile unsigned long long*)&p.counters[2]);
-        }
         epoch = st.epoch;
         if (status == 3) return;                 // watchdog
-        if (status == 1) {
+        if (status == 1 || status == 2) {
           // ordered list of the segment's pending positions (stable compaction of the done flags by the
           // whole grid: every block takes a contiguous slice), written to the list buffer not in use
           uint32_t* pend_list = st.buf ? p.live_b : p.live_c;
@@ -1421,7 +1517,10 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             offset += total;
           }
           bar.sync();
-          if (!kIsGrid || blockIdx.x == 0) serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
+          if (!kIsGrid || blockIdx.x == 0) {
+            if (n_pend <= (unsigned long long)kScanMax) exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes + seg_lo, pend_list, (int)n_pend, p.done + seg_lo);
+            else serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
+          }
           bar.sync();
         }
       }
