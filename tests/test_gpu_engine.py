@@ -151,6 +151,41 @@ def test_proto_wire_format_roundtrip(real_clip):
             assert nb == [list(g["neighbor_id"][no[i]:no[i + 1]]) for i in range(len(nb))]
 
 
+@pytest.mark.parametrize("t", [1, 3])
+def test_short_clips_flush(real_clip, t):
+    """Clips shorter than a chunk: everything is output by PostProcess (dense_segmentation.cpp:286-289)."""
+    clip = real_clip[:t]
+    got, batches, _ = _run_gpu(clip)
+    ref = _run_oracle(clip)
+    _compare(got, ref)
+    assert batches == [0] * t + [t]
+
+
+def test_padded_row_stride_matches_contiguous(real_clip):
+    """VideoFrame rows are padded to a multiple of 4 bytes (width_step); the result must not depend on it."""
+    from video_segment_b200.unit import DenseSegmentationUnit
+    clip = real_clip[:6, :, :135]                       # 135 * 3 = 405 bytes per row -> width_step 408
+    h, w = clip[0].shape[:2]
+    outs = []
+    for pad in (False, True):
+        u = DenseSegmentationUnit(want_id_maps=True)
+        assert u.open_streams(w, h)
+        res = []
+        for f in clip:
+            if pad:
+                buf = np.zeros((h, 408), np.uint8)
+                buf[:, :405] = f.reshape(h, 405)
+                view = np.lib.stride_tricks.as_strided(buf, shape=(h, w, 3), strides=(408, 3, 1))
+                res += u.process_frame(view, width_step=408)
+            else:
+                res += u.process_frame(np.ascontiguousarray(f))
+        res += u.post_process()
+        u.close()
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert np.array_equal(a["id_map"], b["id_map"])
+
+
 def test_error_behaviour():
     from video_segment_b200.unit import DenseSegmentationOptions, DenseSegmentationUnit
     u = DenseSegmentationUnit()

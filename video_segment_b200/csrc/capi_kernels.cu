@@ -158,7 +158,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.live_c = (uint32_t*)dalloc(max_bucket * 16);
     mp.done = (unsigned char*)dalloc(max_bucket);
     mp.live_cap = max_bucket;
-    mp.counters = (unsigned long long*)dalloc((16 + 2048) * 8);
+    mp.counters = (unsigned long long*)dalloc((16 + 4096) * 8);
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
     mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 32) * 8) : nullptr;
     if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, s);
@@ -186,7 +186,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     }
     cudaMemsetAsync(mp.res, 0xff, nodes * 8, s);
     cudaMemsetAsync(mp.acc, 0, nodes * 32, s);
-    cudaMemsetAsync(mp.counters, 0, (16 + 2048) * 8, s);
+    cudaMemsetAsync(mp.counters, 0, (16 + 4096) * 8, s);
     if ((rc = launch_init_iota(mp.cl, (long long)nodes, s))) break;
     if ((rc = launch_init_hull(mp.hull, (long long)nodes, s))) break;
     rc = launch_merge(mp, s);

@@ -163,13 +163,13 @@ int vsb200_dense::init() {
   ENG_CUDA(cudaMalloc(&mp.acc, nodes * 32));
   ENG_CUDA(cudaMalloc(&mp.cl, nodes * 4));
   ENG_CUDA(cudaMalloc(&mp.hull, nodes * sizeof(NodeScratch)));
-  ENG_CUDA(cudaMalloc(&mp.counters, (16 + 2048) * 8));   // + per-block counts of the ordered compaction
+  ENG_CUDA(cudaMalloc(&mp.counters, (16 + 4096) * 8));   // + per-block counts of the ordered compaction
   mp.stats = mp.counters + 8;
   mp.debug = nullptr;
   mp.trace = nullptr;
   ENG_CUDA(cudaMemsetAsync(mp.res, 0xff, nodes * 8, stream));
   ENG_CUDA(cudaMemsetAsync(mp.acc, 0, nodes * 32, stream));
-  ENG_CUDA(cudaMemsetAsync(mp.counters, 0, (16 + 2048) * 8, stream));
+  ENG_CUDA(cudaMemsetAsync(mp.counters, 0, (16 + 4096) * 8, stream));
   ENG_RC(launch_init_iota(mp.cl, (long long)nodes, stream));
   ENG_RC(launch_init_hull(mp.hull, (long long)nodes, stream));
   ENG_CUDA(cudaMalloc(&d_labels, nodes * sizeof(int)));
@@ -495,6 +495,8 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   if (mp.debug) ENG_CUDA(cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, stream));
   ENG_RC(launch_merge(mp, stream));
   if (mp.debug && dbg_path) {
+    unsigned long long h_scan = 0;
+    cudaMemcpyAsync(&h_scan, mp.stats + 3, 8, cudaMemcpyDeviceToHost, stream);
     std::vector<unsigned long long> dbg(kNumBuckets * 4 + 32);
     ENG_CUDA(cudaMemcpyAsync(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost, stream));
     ENG_CUDA(cudaStreamSynchronize(stream));
@@ -510,6 +512,8 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
       const unsigned long long* c = &dbg[kNumBuckets * 4 + 8];
       fprintf(f, "uncertified edge-attempts: hubhub %llu con %llu hubs3 %llu hubless_fin %llu hubless_diam %llu race %llu hub_not_frozen %llu bigmass %llu\n",
               c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
+      fprintf(f, "phase ms: raw_prune %.1f certify %.1f ordered_rounds %.1f scan_serial %.1f hubhub_refresh %.1f; exact scans %llu\n",
+              c[12] / 1e6, c[13] / 1e6, c[14] / 1e6, c[15] / 1e6, c[16] / 1e6, h_scan);
       fprintf(f, "hub_not_frozen reasons: same_id_or_hubs3 %llu con_conflict %llu open_hubs3 %llu bound %llu\n", c[8], c[9], c[10], c[11]);
       fclose(f);
     }

@@ -791,7 +791,8 @@ constexpr int kScHubs3 = 4;      // sub-cluster touches more than two hubs
 constexpr int kScUnc = 8;        // hub: may meet another un-finalised hub through a shared sub-cluster
 constexpr int kScUncAny = 16;    // hub: may meet a hub with the same constraint id through a shared sub-cluster (flags do not matter)
 constexpr unsigned long long kWindowTarget = 1ull << 18;   // live edges aimed at per window
-constexpr unsigned long long kWindowMin = 4096;            // windows are not halved below this many raw edges
+constexpr unsigned long long kWindowMin = 4096;            // smallest raw window
+constexpr unsigned long long kSegmentMin = 2048;           // segments are not halved below this many live edges
 constexpr unsigned long long kResidualSplit = 4096;        // uncertified edges that trigger a halving
 constexpr int kP1U = 8;                                     // edges per thread in flight in the prune pass
 
@@ -1038,11 +1039,12 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
     const uint32_t* src = st.from_master ? master : (st.buf ? p.live_b : p.live_c);
     unsigned long long* dst_cnt = &p.counters[st.buf];
     // ---- P1: find roots, drop inert edges, reserve ----
-    for (unsigned long long i = tid; i < st.n_src; i += nthr) {
+    const unsigned long long i_begin = st.from_master ? seg_lo : 0ull, i_end = st.from_master ? seg_hi : st.n_src;
+    for (unsigned long long i = i_begin + tid; i < i_end; i += nthr) {
       const uint4 e0 = reinterpret_cast<const uint4*>(src)[i];
       const uint32_t code = e0.x, pos = e0.w;
       if (st.from_master) {
-        if (!(pos >= seg_lo && pos < seg_hi) || p.done[pos]) continue;
+        if (p.done[pos]) continue;
       } else if (code == kDone) continue;          // executed in the previous round's commit
       // the entry carries the roots of an earlier pass: climbing from them is shorter than from the voxels
       const int ru = uf_find(p.parent, (int)e0.y), rv = uf_find(p.parent, (int)e0.z);
@@ -1131,6 +1133,9 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
 // counters: [0] live count of buffer A, [1] of buffer B, [2] round epoch, [3] serial result flag,
 //           [4] first hub-hub position of the window, [5] uncertified edge count, [6] window tag
 // live entry = 4 words: code, ru, rv, position in the window
+// development tap: wall time per phase (global thread 0), added to debug[kNumBuckets * 4 + 20 + slot]
+#define VSB_PHASE(slot) do { if (p.debug && tid == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.debug[kNumBuckets * 4 + 20 + (slot)] += t_ - t_phase; t_phase = t_; } } while (0)
+
 template <class Bar, bool kIsGrid>
 __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, const unsigned tid, const unsigned nthr,
                            const int b, const uint32_t* bucket_codes, const unsigned long long bucket_edges) {
@@ -1149,81 +1154,117 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
   unsigned long long raw = min(bucket_edges, kWindowTarget);
   unsigned long long guard = 0;
   uint32_t* const master = p.live_a;            // live list of the window (code, ru, rv, position)
+  unsigned long long t_phase = 0;
+  if (p.debug && tid == 0 && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_phase));
   const unsigned lane = threadIdx.x & 31u;
   while (w0 < bucket_edges) {
     const unsigned long long n_edges = min(raw, bucket_edges - w0);
     const uint32_t* codes = bucket_codes + w0;
-    if (tid == 0) { p.counters[0] = 0ull; p.counters[4] = ~0ull; }
+    if (tid == 0) p.counters[4] = ~0ull;
+    // ---- P1: roots, inert edges, first hub-hub edge -> the window's live list in REFERENCE ORDER.
+    // Every warp takes a contiguous chunk of positions (kP1U x 32 edges in flight: the pass is bound by
+    // the latency of the dependent parent / record loads), stages the survivors at their position and
+    // counts them; after a barrier the chunks are compacted behind each other (stable). ----
+    const unsigned n_warps = nthr >> 5, gw = tid >> 5;
+    const unsigned long long chunk = (((n_edges + n_warps - 1) / n_warps) + 31ull) & ~31ull;
+    const unsigned long long c0 = min(n_edges, (unsigned long long)gw * chunk), c1 = min(n_edges, c0 + chunk);
+    uint4* const staging = reinterpret_cast<uint4*>(p.live_c);
+    uint32_t* const keep_mask = p.live_b;                         // one word per 32 positions
+    uint32_t* const hub_mask = p.live_b + (n_edges >> 5) + 1;
+    unsigned long long* const warp_cnt = p.counters + 16;
+    {
+      unsigned my_count = 0;
+      for (unsigned long long base = c0; base < c1; base += 32ull * kP1U) {
+        uint32_t code[kP1U];
+        int us[kP1U], vs[kP1U], pu[kP1U], pv[kP1U], rus[kP1U], rvs[kP1U];
+        bool in[kP1U], keep[kP1U], hubf[kP1U];
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          const unsigned long long i = base + 32ull * k + lane;
+          in[k] = i < c1;
+          code[k] = in[k] ? __ldg(&codes[i]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          us[k] = 0; vs[k] = 0;
+          if (in[k]) decode_edge(p, code[k], us[k], vs[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) { pu[k] = p.parent[us[k]]; pv[k] = p.parent[vs[k]]; }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          rus[k] = (pu[k] == us[k]) ? us[k] : uf_find(p.parent, pu[k]);
+          rvs[k] = (pv[k] == vs[k]) ? vs[k] : uf_find(p.parent, pv[k]);
+          if (in[k]) {
+            if (pu[k] != us[k] && rus[k] != pu[k]) p.parent[us[k]] = rus[k];     // path compression
+            if (pv[k] != vs[k] && rvs[k] != pv[k]) p.parent[vs[k]] = rvs[k];
+          }
+        }
+        int4 a0[kP1U], b0[kP1U];      // first halves of the two records (sz, con, d0, d1) and fin words
+        int af[kP1U], bf[kP1U];
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          const bool need = in[k] && rus[k] != rvs[k];
+          const int ia = need ? rus[k] : 0, ib = need ? rvs[k] : 0;
+          a0[k] = reinterpret_cast<const int4*>(&p.rec[ia])[0]; af[k] = p.rec[ia].fin;
+          b0[k] = reinterpret_cast<const int4*>(&p.rec[ib])[0]; bf[k] = p.rec[ib].fin;
+        }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {
+          keep[k] = false; hubf[k] = false;
+          if (!in[k]) continue;
+          const unsigned long long i = base + 32ull * k + lane;
+          bool drop = (rus[k] == rvs[k]);
+          if (!drop) {
+            const int asz = a0[k].x, acon = a0[k].y, bsz = b0[k].x, bcon = b0[k].y;
+            const bool both_con = (acon >= 0 && bcon >= 0);
+            drop = (both_con && acon != bcon)
+                   || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
+            hubf[k] = !drop && asz >= mins && bsz >= mins;
+          }
+          p.done[i] = drop ? 1 : 0;                // done flags of the window are (re)written here
+          keep[k] = !drop;
+          if (!drop) staging[i] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
+        }
+#pragma unroll
+        for (int k = 0; k < kP1U; ++k) {           // warp-uniform: chunk bounds are multiples of 32
+          const unsigned long long g0 = base + 32ull * k;
+          const unsigned m = __ballot_sync(0xffffffffu, keep[k]);
+          const unsigned m2 = __ballot_sync(0xffffffffu, hubf[k]);
+          if (lane == 0 && g0 < c1) { keep_mask[g0 >> 5] = m; hub_mask[g0 >> 5] = m2; }
+          my_count += __popc(m);
+        }
+      }
+      if (lane == 0) warp_cnt[gw] = my_count;
+    }
     bar.sync();
-    // ---- P1: roots, inert edges, first hub-hub edge.  kP1U edges per thread are in flight
-    // together (the pass is bound by the latency of the dependent parent / record loads) ----
-    for (unsigned long long i0 = tid; i0 < n_edges; i0 += (unsigned long long)nthr * kP1U) {
-      uint32_t code[kP1U];
-      int us[kP1U], vs[kP1U], pu[kP1U], pv[kP1U], rus[kP1U], rvs[kP1U];
-      bool in[kP1U];
-#pragma unroll
-      for (int k = 0; k < kP1U; ++k) {
-        const unsigned long long i = i0 + (unsigned long long)k * nthr;
-        in[k] = i < n_edges;
-        code[k] = in[k] ? __ldg(&codes[i]) : 0u;
-      }
-#pragma unroll
-      for (int k = 0; k < kP1U; ++k) {
-        us[k] = 0; vs[k] = 0;
-        if (in[k]) decode_edge(p, code[k], us[k], vs[k]);
-      }
-#pragma unroll
-      for (int k = 0; k < kP1U; ++k) { pu[k] = p.parent[us[k]]; pv[k] = p.parent[vs[k]]; }
-#pragma unroll
-      for (int k = 0; k < kP1U; ++k) {
-        rus[k] = (pu[k] == us[k]) ? us[k] : uf_find(p.parent, pu[k]);
-        rvs[k] = (pv[k] == vs[k]) ? vs[k] : uf_find(p.parent, pv[k]);
-        if (in[k]) {
-          if (pu[k] != us[k] && rus[k] != pu[k]) p.parent[us[k]] = rus[k];     // path compression
-          if (pv[k] != vs[k] && rvs[k] != pv[k]) p.parent[vs[k]] = rvs[k];
+    unsigned long long n_master = 0;
+    {
+      unsigned long long before = 0, total = 0;
+      for (unsigned j = lane; j < n_warps; j += 32) { const unsigned long long c = *((volatile unsigned long long*)&warp_cnt[j]); total += c; if (j < gw) before += c; }
+      for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+      n_master = total;
+      unsigned long long off = before;
+      for (unsigned long long g0 = c0; g0 < c1; g0 += 32) {
+        const unsigned m = keep_mask[g0 >> 5], m2 = hub_mask[g0 >> 5];
+        if ((m >> lane) & 1u) {
+          const unsigned long long idx = off + __popc(m & ((1u << lane) - 1u));
+          reinterpret_cast<uint4*>(master)[idx] = staging[g0 + lane];
+          if ((m2 >> lane) & 1u) atomicMin(&p.counters[4], idx);
         }
-      }
-      int4 a0[kP1U], b0[kP1U];      // first halves of the two records (sz, con, d0, d1) and fin words
-      int af[kP1U], bf[kP1U];
-#pragma unroll
-      for (int k = 0; k < kP1U; ++k) {
-        const bool need = in[k] && rus[k] != rvs[k];
-        const int ia = need ? rus[k] : 0, ib = need ? rvs[k] : 0;
-        a0[k] = reinterpret_cast<const int4*>(&p.rec[ia])[0]; af[k] = p.rec[ia].fin;
-        b0[k] = reinterpret_cast<const int4*>(&p.rec[ib])[0]; bf[k] = p.rec[ib].fin;
-      }
-#pragma unroll
-      for (int k = 0; k < kP1U; ++k) {
-        if (!in[k]) continue;
-        const unsigned long long i = i0 + (unsigned long long)k * nthr;
-        bool drop = (rus[k] == rvs[k]);
-        bool hubhub = false;
-        if (!drop) {
-          const int asz = a0[k].x, acon = a0[k].y, bsz = b0[k].x, bcon = b0[k].y;
-          const bool both_con = (acon >= 0 && bcon >= 0);
-          drop = (both_con && acon != bcon)
-                 || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
-          hubhub = !drop && asz >= mins && bsz >= mins;
-        }
-        p.done[i] = drop ? 1 : 0;                // done flags of the window are (re)written here
-        if (drop) continue;
-        if (hubhub) atomicMin(&p.counters[4], i);
-        const unsigned long long slot = warp_slot(&p.counters[0]);
-        if (slot < p.live_cap)
-          reinterpret_cast<uint4*>(master)[slot] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
+        off += __popc(m);
       }
     }
     bar.sync();
-    unsigned long long n_master = *((volatile unsigned long long*)&p.counters[0]);
-    if (n_master > p.live_cap) n_master = p.live_cap;   // cannot happen: cap = largest bucket
-    unsigned long long hh = *((volatile unsigned long long*)&p.counters[4]);   // first live edge between two hubs
-    // ---------------- segments of the window: [seg_lo, seg_hi) in window positions ----------------
-    unsigned long long seg_lo = 0, seg_len = n_edges;
+    VSB_PHASE(0);                                  // raw prune pass
+    unsigned long long hh = *((volatile unsigned long long*)&p.counters[4]);   // index of the first live edge between two hubs
+    // ---------------- segments of the window: [seg_lo, seg_hi) are INDICES into the ordered live list ----------------
+    unsigned long long seg_lo = 0, seg_len = n_master;
     bool any_split = false;
     unsigned long long unc_sum = 0;
-    while (n_master != 0 && seg_lo < n_edges) {
+    while (seg_lo < n_master) {
       if (++guard > (1ull << 22)) { if (tid == 0) { printf("vsb200 merge: window watchdog bucket %d\n", b); p.stats[7] = 1ull; } return; }
-      const unsigned long long seg_end = min(min(hh, n_edges), seg_lo + seg_len);   // a hub-hub edge ends the segment in front of it
+      const unsigned long long seg_end = min(min(hh, n_master), seg_lo + seg_len);   // a hub-hub edge ends the segment in front of it
       unsigned long long seg_hi = seg_end;
       bool have_live = false;
       // ---- certification of [seg_lo, seg_hi), halving the segment while too much stays uncertified ----
@@ -1231,11 +1272,11 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         ++wtag;
         if (tid == 0) { p.counters[5] = 0ull; p.counters[7] = 0ull; }
         bar.sync();
-#define VSB_IN_SEG(e) ((e).w >= seg_lo && (e).w < seg_hi && !p.done[(e).w])
+#define VSB_IN_SEG(e) (!p.done[(e).w])
         // ---- C1: sub-clusters of small atoms ----
         {
           unsigned long long mine = 0;
-          for (unsigned long long i = tid; i < n_master; i += nthr) {
+          for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
             const uint4 e = reinterpret_cast<const uint4*>(master)[i];
             if (!VSB_IN_SEG(e)) continue;
             ++mine;
@@ -1251,9 +1292,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         // sit next to each other in reference order: lanes that update the same record are combined
         // with __match_any_sync / __reduce_*_sync, one atomic per group. ----
         const int tag_a = 2 * wtag, tag_b = 2 * wtag + 1;
-        for (unsigned long long i0 = tid - lane; i0 < n_master; i0 += nthr) {
+        for (unsigned long long i0 = seg_lo + (tid - lane); i0 < seg_hi; i0 += nthr) {
           const unsigned long long i = i0 + lane;
-          bool in = i < n_master;
+          bool in = i < seg_hi;
           uint4 e = make_uint4(kDone, 0u, 0u, 0u);
           if (in) { e = reinterpret_cast<const uint4*>(master)[i]; in = VSB_IN_SEG(e); }
           int hub = -1, sub = -1;
@@ -1308,9 +1349,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         }
         bar.sync();
         // ---- C3: what every hub may absorb in this segment (once per atom and hub) ----
-        for (unsigned long long i0 = tid - lane; i0 < n_master; i0 += nthr) {
+        for (unsigned long long i0 = seg_lo + (tid - lane); i0 < seg_hi; i0 += nthr) {
           const unsigned long long i = i0 + lane;
-          bool in = i < n_master;
+          bool in = i < seg_hi;
           uint4 e = make_uint4(kDone, 0u, 0u, 0u);
           if (in) { e = reinterpret_cast<const uint4*>(master)[i]; in = VSB_IN_SEG(e); }
 #pragma unroll
@@ -1393,7 +1434,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         // ---- C4: count the edges the certificates do not cover ----
         {
           unsigned long long mine = 0;
-          for (unsigned long long i = tid; i < n_master; i += nthr) {
+          for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
             const uint4 e = reinterpret_cast<const uint4*>(master)[i];
             if (!VSB_IN_SEG(e)) continue;
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
@@ -1411,10 +1452,10 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         }
         bar.sync();
         const unsigned long long n_unc = *((volatile unsigned long long*)&p.counters[5]);
-        const bool split = (n_unc > kResidualSplit && seg_hi - seg_lo > kWindowMin);
+        const bool split = (n_unc > kResidualSplit && seg_hi - seg_lo > kSegmentMin);
         // ---- C5: apply the certified merges (skipped when the segment is halved) ----
         if (!split) {
-          for (unsigned long long i = tid; i < n_master; i += nthr) {
+          for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
             const uint4 e = reinterpret_cast<const uint4*>(master)[i];
             if (!VSB_IN_SEG(e)) continue;
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;    // sizes are not folded before the next barrier
@@ -1448,9 +1489,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         }
         bar.sync();
         // ---- C6: fold the bulk contributions, scratch back to idle ----
-        for (unsigned long long i = tid; i < n_master; i += nthr) {
+        for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
           const uint4 e = reinterpret_cast<const uint4*>(master)[i];
-          if (!(e.w >= seg_lo && e.w < seg_hi)) continue;
           const unsigned char dn = p.done[e.w];
           if (dn == 1) continue;                  // was not part of this attempt
 #pragma unroll
@@ -1466,10 +1506,18 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         bar.sync();
         if (!split) { unc_sum += n_unc; break; }
         any_split = true;
-        seg_hi = seg_lo + (seg_hi - seg_lo + 1) / 2;
-        seg_len = seg_hi - seg_lo;
+        {
+          // shrink in proportion to the excess (at least by half): uncertified edges cluster around a few hubs
+          const unsigned long long len = seg_hi - seg_lo;
+          unsigned long long nl = len * kResidualSplit / n_unc;
+          nl = min(nl, (len + 1) / 2);
+          nl = max(nl, kSegmentMin);
+          seg_hi = seg_lo + nl;
+          seg_len = nl;
+        }
       }
 #undef VSB_IN_SEG
+      VSB_PHASE(1);                                // certification attempts
       // ---------------- ordered rounds on what is left of the segment ----------------
       if (have_live) {
         RoundState st;
@@ -1481,6 +1529,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         int status = ordered_rounds<Bar>(p, bar, tid, nthr, b, edge_w, wtag, master, seg_lo, seg_hi, st,
                                          (kIsGrid && !(p.dev_flags & 4)) ? kBlockRoundsLimit : 0ull, kSerialSwitch, guard);
         epoch = st.epoch;
+        VSB_PHASE(2);                              // ordered rounds
         if (status == 3) return;                 // watchdog
         if (status == 1 || status == 2) {
           // ordered list of the segment's pending positions (stable compaction of the done flags by the
@@ -1489,12 +1538,11 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           const unsigned nblk = kIsGrid ? gridDim.x : 1u, blk = kIsGrid ? blockIdx.x : 0u;
           const unsigned long long range = seg_hi - seg_lo;
           const unsigned long long slice = (range + nblk - 1) / nblk;
-          const unsigned long long s_lo = min(range, (unsigned long long)blk * slice), s_hi = min(range, s_lo + slice);
-          const unsigned char* dflags = p.done + seg_lo;
+          const unsigned long long s_lo = seg_lo + min(range, (unsigned long long)blk * slice), s_hi = min(seg_hi, s_lo + slice);
           unsigned long long* blockcnt = p.counters + 16;
           {
             unsigned cnt = 0;
-            for (unsigned long long i = s_lo + threadIdx.x; i < s_hi; i += blockDim.x) cnt += (dflags[i] == 0) ? 1u : 0u;
+            for (unsigned long long i = s_lo + threadIdx.x; i < s_hi; i += blockDim.x) cnt += (p.done[master[4 * i + 3]] == 0) ? 1u : 0u;
             for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             if ((threadIdx.x & 31) == 0) S.warp_cnt[threadIdx.x >> 5] = cnt;
             __syncthreads();
@@ -1510,39 +1558,43 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           for (unsigned k = 0; k < nblk; ++k) { const unsigned long long c = *((volatile unsigned long long*)&blockcnt[k]); if (k < blk) offset += c; n_pend += c; }
           for (unsigned long long base = s_lo; base < s_hi; base += blockDim.x) {
             const unsigned long long i = base + threadIdx.x;
-            const bool flag = (i < s_hi) && (dflags[i] == 0);
+            uint32_t pos = 0;
+            bool flag = false;
+            if (i < s_hi) { pos = master[4 * i + 3]; flag = (p.done[pos] == 0); }
             unsigned total;
             const unsigned rank = block_rank(S, flag, &total);
-            if (flag) pend_list[offset + rank] = (uint32_t)i;
+            if (flag) pend_list[offset + rank] = pos;
             offset += total;
           }
           bar.sync();
           if (!kIsGrid || blockIdx.x == 0) {
-            if (n_pend <= (unsigned long long)kScanMax) exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes + seg_lo, pend_list, (int)n_pend, p.done + seg_lo);
-            else serial_rounds(p, S, b, codes + seg_lo, pend_list, n_pend, wtag, p.done + seg_lo);
+            if (n_pend <= (unsigned long long)kScanMax) exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, pend_list, (int)n_pend, p.done);
+            else serial_rounds(p, S, b, codes, pend_list, n_pend, wtag, p.done);
           }
           bar.sync();
+          VSB_PHASE(3);                            // compaction + exact scan / serial window mode
         }
       }
       // ---- the hub-hub edge that ended the segment runs alone, exactly (a real big-big decision) ----
-      const bool at_hubhub = (seg_hi == hh && hh < n_edges);
+      const bool at_hubhub = (seg_hi == hh && hh < n_master);
       if (at_hubhub && tid == 0) {
-        int u, v;
-        decode_edge(p, codes[hh], u, v);
-        const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
-        if (ru != rv) exec_strict(p, ru, rv, edge_w, p.stats);
-        p.done[hh] = 1;
+        const uint4 e = reinterpret_cast<const uint4*>(master)[hh];
+        if (!p.done[e.w]) {
+          const int ru = uf_find(p.parent, (int)e.y), rv = uf_find(p.parent, (int)e.z);
+          if (ru != rv) exec_strict(p, ru, rv, edge_w, p.stats);
+          p.done[e.w] = 1;
+        }
       }
       seg_lo = at_hubhub ? hh + 1 : seg_hi;
-      if (seg_lo >= n_edges) break;
-      if (seg_hi == seg_end) seg_len = min(seg_len * 2, n_edges);     // the whole planned segment went through: grow again
+      if (seg_lo >= n_master) break;
+      if (seg_hi == seg_end) seg_len = min(seg_len * 2, n_master);     // the whole planned segment went through: grow again
       // ---- refresh: roots of the entries still ahead, drop what became inert, next hub-hub edge ----
       if (tid == 0) p.counters[4] = ~0ull;
       ++epoch;
       bar.sync();
-      for (unsigned long long i = tid; i < n_master; i += nthr) {
+      for (unsigned long long i = seg_lo + tid; i < n_master; i += nthr) {
         uint4 e = reinterpret_cast<const uint4*>(master)[i];
-        if (e.w < seg_lo || p.done[e.w]) continue;
+        if (p.done[e.w]) continue;
         const int ru = uf_find(p.parent, (int)e.y), rv = uf_find(p.parent, (int)e.z);
         bool drop = (ru == rv);
         bool hubhub = false;
@@ -1553,11 +1605,12 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           hubhub = !drop && A.sz >= mins && B.sz >= mins;
         }
         if (drop) { p.done[e.w] = 1; continue; }
-        if (hubhub) atomicMin(&p.counters[4], (unsigned long long)e.w);
+        if (hubhub) atomicMin(&p.counters[4], i);
         if (ru != (int)e.y || rv != (int)e.z) { e.y = (uint32_t)ru; e.z = (uint32_t)rv; reinterpret_cast<uint4*>(master)[i] = e; }
       }
       bar.sync();
       hh = *((volatile unsigned long long*)&p.counters[4]);
+      VSB_PHASE(4);                                // hub-hub edge + refresh
     }
     // next window: aim at kWindowTarget live edges
     w0 += n_edges;
