@@ -512,8 +512,8 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
       const unsigned long long* c = &dbg[kNumBuckets * 4 + 8];
       fprintf(f, "uncertified edge-attempts: hubhub %llu con %llu hubs3 %llu hubless_fin %llu hubless_diam %llu race %llu hub_not_frozen %llu bigmass %llu\n",
               c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
-      fprintf(f, "phase ms: raw_prune %.1f certify %.1f ordered_rounds %.1f scan_serial %.1f hubhub_refresh %.1f; exact scans %llu\n",
-              c[12] / 1e6, c[13] / 1e6, c[14] / 1e6, c[15] / 1e6, c[16] / 1e6, h_scan);
+      fprintf(f, "phase ms: raw_prune %.1f certify %.1f ordered_rounds %.1f compaction %.1f hubhub_refresh %.1f exact_scan %.1f serial_mode %.1f; exact scans %llu (%llu edges), serial calls %llu (%llu edges)\n",
+              c[12] / 1e6, c[13] / 1e6, c[14] / 1e6, c[15] / 1e6, c[16] / 1e6, c[17] / 1e6, c[18] / 1e6, h_scan, c[19], c[20], c[21]);
       fprintf(f, "hub_not_frozen reasons: same_id_or_hubs3 %llu con_conflict %llu open_hubs3 %llu bound %llu\n", c[8], c[9], c[10], c[11]);
       fclose(f);
     }

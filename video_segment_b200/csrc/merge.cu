@@ -908,7 +908,7 @@ __device__ int subcluster_why(const MergeParams& p, const NodeScratch& S, const 
   return 7;
 }
 
-constexpr unsigned long long kBlockRoundsLimit = 1024;   // residual lists up to this size are finished by block 0 alone
+constexpr unsigned long long kBlockRoundsLimit = 2048;   // residual lists up to this size (= kScanMax) are finished by block 0 alone
 
 // ---------------------------------------------------------------------------------------------
 // Exact scan.  A small residual (<= kScanMax pending edges of one segment, in reference order) is
@@ -918,15 +918,28 @@ constexpr unsigned long long kBlockRoundsLimit = 1024;   // residual lists up to
 // result back.  Cost ~ 0.1 us per edge, independent of the dependency depth (an ordered round costs
 // three grid barriers plus several dependent global loads, and a chain needs one round per link).
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanMax = 1024;
+constexpr int kScanMax = 2048;
+constexpr int kScanHashBits = 13;                // 4 * kScanMax slots
+static_assert((1 << kScanHashBits) == 4 * kScanMax, "hash size");
+struct ScanShared;
+__device__ __forceinline__ RegionRec scan_load(const int2 (*rec)[3], int j) {
+  const int2 a = rec[j][0], b = rec[j][1], c = rec[j][2];
+  RegionRec o;
+  o.sz = a.x; o.con = a.y; o.d0 = __int_as_float(b.x); o.d1 = __int_as_float(b.y); o.d2 = __int_as_float(c.x); o.fin = c.y; o.pad0 = o.pad1 = 0;
+  return o;
+}
+__device__ __forceinline__ void scan_store(int2 (*rec)[3], int j, const RegionRec& o) {
+  rec[j][0] = make_int2(o.sz, o.con);
+  rec[j][1] = make_int2(__float_as_int(o.d0), __float_as_int(o.d1));
+  rec[j][2] = make_int2(__float_as_int(o.d2), o.fin);
+}
 struct ScanShared {
   unsigned short ea[kScanMax], eb[kScanMax];       // local ids of an edge's two roots
   uint32_t epos[kScanMax];
   int tru[kScanMax], trv[kScanMax];                 // global roots of an edge (staging)
   int gid[2 * kScanMax];                            // local id -> global root
   unsigned short par[2 * kScanMax];                 // local union-find
-  int sz[2 * kScanMax], con[2 * kScanMax], fin[2 * kScanMax];
-  float d0[2 * kScanMax], d1[2 * kScanMax], d2[2 * kScanMax];
+  int2 rec[2 * kScanMax][3];                        // 24-byte records (sz, con | d0, d1 | d2, fin): three 64-bit shared accesses each
   unsigned hkey[4 * kScanMax];                      // hash: global root + 1 (0 = empty)
   unsigned short hidx[4 * kScanMax];                // local id of the slot's root
   int n_roots;
@@ -935,7 +948,7 @@ static_assert(sizeof(ScanShared) <= sizeof(SerialShared), "ScanShared overlays S
 
 // phase 1 (insert) and phase 2 (lookup, after a block barrier) of the root -> local id hash
 __device__ __forceinline__ void scan_insert(ScanShared& C, unsigned root) {
-  unsigned slot = (root * 2654435761u) >> 20;       // 12 bits
+  unsigned slot = (root * 2654435761u) >> (32 - kScanHashBits);       // kScanHashBits bits
   while (true) {
     const unsigned k = atomicCAS(&C.hkey[slot], 0u, root + 1u);
     if (k == 0u) {
@@ -949,7 +962,7 @@ __device__ __forceinline__ void scan_insert(ScanShared& C, unsigned root) {
   }
 }
 __device__ __forceinline__ unsigned short scan_lookup(const ScanShared& C, unsigned root) {
-  unsigned slot = (root * 2654435761u) >> 20;
+  unsigned slot = (root * 2654435761u) >> (32 - kScanHashBits);
   while (C.hkey[slot] != root + 1u) slot = (slot + 1u) & (4 * kScanMax - 1);
   return C.hidx[slot];
 }
@@ -980,9 +993,8 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
   __syncthreads();
   const int n_roots = C.n_roots;
   for (int j = tid; j < n_roots; j += nthr) {
-    const RegionRec R = load_rec(&p.rec[C.gid[j]]);
     C.par[j] = (unsigned short)j;
-    C.sz[j] = R.sz; C.con[j] = R.con; C.fin[j] = R.fin; C.d0[j] = R.d0; C.d1[j] = R.d1; C.d2[j] = R.d2;
+    scan_store(C.rec, j, load_rec(&p.rec[C.gid[j]]));
   }
   __syncthreads();
   if (tid == 0) {
@@ -990,12 +1002,10 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
     for (int i = 0; i < n_pend; ++i) {
       const int a = findl(C.ea[i]), bq = findl(C.eb[i]);
       if (a == bq) continue;
-      RegionRec A, B;
-      A.sz = C.sz[a]; A.con = C.con[a]; A.fin = C.fin[a]; A.d0 = C.d0[a]; A.d1 = C.d1[a]; A.d2 = C.d2[a]; A.pad0 = A.pad1 = 0;
-      B.sz = C.sz[bq]; B.con = C.con[bq]; B.fin = C.fin[bq]; B.d0 = C.d0[bq]; B.d1 = C.d1[bq]; B.d2 = C.d2[bq]; B.pad0 = B.pad1 = 0;
+      RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
       const int r = decide_pair(p, A, B, edge_w);      // rep_1 = root of region_1 (the anchor), as in the reference
-      C.sz[a] = A.sz; C.con[a] = A.con; C.fin[a] = A.fin; C.d0[a] = A.d0; C.d1[a] = A.d1; C.d2[a] = A.d2;
-      C.sz[bq] = B.sz; C.con[bq] = B.con; C.fin[bq] = B.fin; C.d0[bq] = B.d0; C.d1[bq] = B.d1; C.d2[bq] = B.d2;
+      if (r != 2) scan_store(C.rec, a, A);              // survivor, or flags / constraint changed without a merge
+      if (r != 1) scan_store(C.rec, bq, B);
       if (r == 1) C.par[bq] = (unsigned short)a;
       else if (r == 2) C.par[a] = (unsigned short)bq;
     }
@@ -1006,9 +1016,7 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
     while (C.par[x] != x) x = C.par[x];
     const int g = C.gid[j];
     if (x == j) {
-      RegionRec R;
-      R.sz = C.sz[j]; R.con = C.con[j]; R.fin = C.fin[j]; R.d0 = C.d0[j]; R.d1 = C.d1[j]; R.d2 = C.d2[j]; R.pad0 = R.pad1 = 0;
-      store_rec(&p.rec[g], R);
+      store_rec(&p.rec[g], scan_load(C.rec, j));
     } else {
       p.parent[g] = C.gid[x];
     }
@@ -1555,7 +1563,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           }
           bar.sync();
           unsigned long long offset = 0, n_pend = 0;
-          for (unsigned k = 0; k < nblk; ++k) { const unsigned long long c = *((volatile unsigned long long*)&blockcnt[k]); if (k < blk) offset += c; n_pend += c; }
+          for (unsigned k = lane; k < nblk; k += 32) { const unsigned long long c = *((volatile unsigned long long*)&blockcnt[k]); if (k < blk) offset += c; n_pend += c; }
+          for (int o = 16; o > 0; o >>= 1) { offset += __shfl_xor_sync(0xffffffffu, offset, o); n_pend += __shfl_xor_sync(0xffffffffu, n_pend, o); }
           for (unsigned long long base = s_lo; base < s_hi; base += blockDim.x) {
             const unsigned long long i = base + threadIdx.x;
             uint32_t pos = 0;
@@ -1567,12 +1576,19 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             offset += total;
           }
           bar.sync();
+          VSB_PHASE(3);                            // ordered compaction of the pending positions
           if (!kIsGrid || blockIdx.x == 0) {
-            if (n_pend <= (unsigned long long)kScanMax) exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, pend_list, (int)n_pend, p.done);
-            else serial_rounds(p, S, b, codes, pend_list, n_pend, wtag, p.done);
+            if (n_pend <= (unsigned long long)kScanMax || !(p.dev_flags & 8)) {
+              // the pending edges in reference order, kScanMax at a time (each batch reloads the current roots)
+              for (unsigned long long q0 = 0; q0 < n_pend; q0 += kScanMax)
+                exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, pend_list + q0, (int)min((unsigned long long)kScanMax, n_pend - q0), p.done);
+            } else serial_rounds(p, S, b, codes, pend_list, n_pend, wtag, p.done);
           }
           bar.sync();
-          VSB_PHASE(3);                            // compaction + exact scan / serial window mode
+          if (p.debug && tid == 0 && blockIdx.x == 0) {
+            if (n_pend <= (unsigned long long)kScanMax) { p.debug[kNumBuckets * 4 + 27] += n_pend; } else { p.debug[kNumBuckets * 4 + 28] += 1ull; p.debug[kNumBuckets * 4 + 29] += n_pend; }
+          }
+          if (n_pend <= (unsigned long long)kScanMax) { VSB_PHASE(5); } else { VSB_PHASE(6); }   // exact scan / serial window mode
         }
       }
       // ---- the hub-hub edge that ended the segment runs alone, exactly (a real big-big decision) ----
