@@ -215,8 +215,7 @@ __device__ __forceinline__ void acc_add(unsigned long long* acc, int root, const
   atomicAdd(&a[1], (unsigned long long)__double2ll_rn((double)r.d0 * kFix) * sz);
   atomicAdd(&a[2], (unsigned long long)__double2ll_rn((double)r.d1 * kFix) * sz);
   atomicAdd(&a[3], (unsigned long long)__double2ll_rn((double)r.d2 * kFix) * sz);
-  __threadfence();
-  atomicAdd(&a[0], sz);
+  atomicAdd(&a[0], sz);                // folds only run behind a barrier: no ordering needed between the four words
 }
 
 // fold pending bulk contributions into the representative's record (size-weighted mean)
@@ -789,6 +788,8 @@ constexpr int kScFin = 1;        // a member is finalised
 constexpr int kScConMulti = 2;   // members / absorbable atoms carry different constraint ids
 constexpr int kScHubs3 = 4;      // sub-cluster touches more than two hubs
 constexpr int kScUnc = 8;        // hub: may meet another un-finalised hub through a shared sub-cluster
+constexpr int kScCertYes = 32;     // cached verdict of subcluster_certified for this segment attempt
+constexpr int kScCertNo = 64;
 constexpr int kScUncAny = 16;    // hub: may meet a hub with the same constraint id through a shared sub-cluster (flags do not matter)
 constexpr unsigned long long kWindowTarget = 1ull << 18;   // live edges aimed at per window
 constexpr unsigned long long kWindowMin = 4096;            // smallest raw window
@@ -1243,14 +1244,24 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           my_count += __popc(m);
         }
       }
-      if (lane == 0) warp_cnt[gw] = my_count;
+      // two-level counts: warps of a block in shared memory, blocks in global memory
+      const unsigned wib = threadIdx.x >> 5;
+      if (lane == 0) S.warp_cnt[wib] = my_count;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < kMergeWarps; ++k) t += S.warp_cnt[k];
+        warp_cnt[kIsGrid ? blockIdx.x : 0u] = t;
+      }
     }
     bar.sync();
     unsigned long long n_master = 0;
     {
+      const unsigned nblk = kIsGrid ? gridDim.x : 1u, blk = kIsGrid ? blockIdx.x : 0u, wib = threadIdx.x >> 5;
       unsigned long long before = 0, total = 0;
-      for (unsigned j = lane; j < n_warps; j += 32) { const unsigned long long c = *((volatile unsigned long long*)&warp_cnt[j]); total += c; if (j < gw) before += c; }
+      for (unsigned j = lane; j < nblk; j += 32) { const unsigned long long c = *((volatile unsigned long long*)&warp_cnt[j]); total += c; if (j < blk) before += c; }
       for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+      for (unsigned k = 0; k < wib; ++k) before += S.warp_cnt[k];
       n_master = total;
       unsigned long long off = before;
       for (unsigned long long g0 = c0; g0 < c1; g0 += 32) {
@@ -1291,7 +1302,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
             if (sa < mins && sb < mins) cl_union(p.cl, (int)e.y, (int)e.z);
           }
-          if (mine) atomicAdd(&p.counters[7], mine);
+          for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+          if (lane == 0 && mine) atomicAdd(&p.counters[7], mine);
         }
         bar.sync();
         if (*((volatile unsigned long long*)&p.counters[7]) == 0ull) break;      // nothing live in this segment
@@ -1376,12 +1388,12 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
                 // hub side of a hub-small edge: a sub-cluster with more than two hubs makes all of them uncertain
                 const int o = s2 ? (int)e.y : (int)e.z;
                 if (p.rec[o].sz < mins) {
-                  const int c = cl_find(p.cl, o);
+                  const int c = cl_find_compress(p.cl, o);
                   if ((p.hull[c].flags & kScHubs3) && (p.hull[r].flags & (kScUnc | kScUncAny)) != (kScUnc | kScUncAny))
                     atomicOr(&p.hull[r].flags, R.con >= 0 ? (kScUnc | kScUncAny) : kScUnc);
                 }
               } else if (atomicExch(&p.hull[r].claim, tag_b) != tag_b) {
-                SC = load_sc(&p.hull[cl_find(p.cl, r)]);
+                SC = load_sc(&p.hull[cl_find_compress(p.cl, r)]);
                 valid = true;
               }
             }
@@ -1391,7 +1403,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             // absorb: the frozen bound then also certifies that their meeting ends in a merge.  Done once per
             // sub-cluster, by the lane that claimed the sub-cluster's root atom.
             bool pair_unc_any = false;
-            if (valid && SC.hub0 >= 0 && SC.hub1 >= 0 && !(SC.flags & kScHubs3) && cl_find(p.cl, s2 ? (int)e.z : (int)e.y) == (s2 ? (int)e.z : (int)e.y)) {
+            if (valid && SC.hub0 >= 0 && SC.hub1 >= 0 && !(SC.flags & kScHubs3) && cl_find_compress(p.cl, s2 ? (int)e.z : (int)e.y) == (s2 ? (int)e.z : (int)e.y)) {
               const RegionRec H0 = load_rec(&p.rec[SC.hub0]), H1 = load_rec(&p.rec[SC.hub1]);
               const bool both_con = H0.con >= 0 && H1.con >= 0;
               bool contribute = false;
@@ -1448,15 +1460,22 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
             bool cert = false;
             if (sa < mins || sb < mins) {
-              const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
-              int target;
-              const NodeScratch SCc = load_sc(&p.hull[c]);
-              cert = subcluster_certified(p, c, SCc, wt, mins, &target);
-              if (!cert && p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8 + subcluster_why(p, SCc, wt, mins)], 1ull);
+              const int c = cl_find_compress(p.cl, sa < mins ? (int)e.y : (int)e.z);
+              // the verdict is a function of the sub-cluster: the first edges to ask compute it, the rest read it
+              const int fl = *((volatile int*)&p.hull[c].flags);
+              if (fl & (kScCertYes | kScCertNo)) cert = (fl & kScCertYes) != 0;
+              else {
+                int target;
+                const NodeScratch SCc = load_sc(&p.hull[c]);
+                cert = subcluster_certified(p, c, SCc, wt, mins, &target);
+                atomicOr(&p.hull[c].flags, cert ? kScCertYes : kScCertNo);
+              }
+              if (!cert && p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8 + subcluster_why(p, load_sc(&p.hull[c]), wt, mins)], 1ull);
             } else if (p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8], 1ull);
             if (!cert) ++mine;
           }
-          if (mine) atomicAdd(&p.counters[5], mine);
+          for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+          if (lane == 0 && mine) atomicAdd(&p.counters[5], mine);
         }
         bar.sync();
         const unsigned long long n_unc = *((volatile unsigned long long*)&p.counters[5]);
@@ -1468,10 +1487,10 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             if (!VSB_IN_SEG(e)) continue;
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;    // sizes are not folded before the next barrier
             if (sa >= mins && sb >= mins) continue;
-            const int c = cl_find(p.cl, sa < mins ? (int)e.y : (int)e.z);
-            int target;
+            const int c = cl_find_compress(p.cl, sa < mins ? (int)e.y : (int)e.z);
             const NodeScratch SC = load_sc(&p.hull[c]);
-            if (!subcluster_certified(p, c, SC, wt, mins, &target)) {
+            const int target = (SC.hub0 >= 0) ? SC.hub0 : c;        // certified sub-clusters touch at most one hub
+            if (!(SC.flags & kScCertYes)) {
               // the ordered rounds may let frozen hubs absorb: publish the certificate
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
