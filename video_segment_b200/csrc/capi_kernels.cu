@@ -159,6 +159,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.done = (unsigned char*)dalloc(max_bucket);
     mp.live_cap = max_bucket;
     mp.counters = (unsigned long long*)dalloc((16 + 4096) * 8);
+    mp.scan_queue = (uint32_t*)dalloc(kScanQueueWords * sizeof(uint32_t));
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
     mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 32) * 8) : nullptr;
     if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, s);
@@ -179,7 +180,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
         }
       });
     }
-    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.live_c || !mp.done || !mp.counters) {
+    if (!mp.res || !mp.acc || !mp.cl || !mp.hull || !mp.live_a || !mp.live_b || !mp.live_c || !mp.done || !mp.counters || !mp.scan_queue) {
       set_error("segment_chunk: out of device memory (merge workspace)");
       rc = VSB200_ERR_CUDA;
       break;

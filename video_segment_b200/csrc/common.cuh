@@ -79,6 +79,7 @@ struct __align__(16) NodeScratch {
   int frozen;                // window tag in which this hub's decision-relevant state is certified constant
 };
 constexpr int kNoCon = 0x7f7f7f7f;
+constexpr size_t kScanQueueWords = 1024 * 2 * 2048;   // up to 1024 CTAs x 2 x kScanMax words
 
 struct MergeParams {
   int w, h, slots;                 // graph geometry; nodes = slots * w * h
@@ -99,6 +100,7 @@ struct MergeParams {
   uint32_t* live_a;                // live edge buffers: (code, ru, rv, position)
   uint32_t* live_b;
   uint32_t* live_c;                // live_a = live list of the window, live_b / live_c = lists of the ordered rounds
+  uint32_t* scan_queue;            // [kScanQueueWords] per-CTA (position, group) queues of the group-parallel exact scans
   unsigned long long live_cap;     // in triples
   unsigned long long* counters;    // [8] device counters
   unsigned long long* stats;       // [8] rounds, commits, safe merges, ...

@@ -112,7 +112,7 @@ struct vsb200_dense {
 void vsb200_dense::release() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_bgr); F(d_pre_scratch); F(d_flows); F(d_codes); F(d_bstart); F(d_sort_scratch); F(d_parent); F(d_rec);
-  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_c); F(mp.done); F(mp.counters); F(mp.debug);
+  F(mp.res); F(mp.acc); F(mp.cl); F(mp.hull); F(mp.live_a); F(mp.live_b); F(mp.live_c); F(mp.done); F(mp.counters); F(mp.debug); F(mp.scan_queue);
   F(d_labels); F(d_roots); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
   F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
   F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
@@ -163,7 +163,8 @@ int vsb200_dense::init() {
   ENG_CUDA(cudaMalloc(&mp.acc, nodes * 32));
   ENG_CUDA(cudaMalloc(&mp.cl, nodes * 4));
   ENG_CUDA(cudaMalloc(&mp.hull, nodes * sizeof(NodeScratch)));
-  ENG_CUDA(cudaMalloc(&mp.counters, (16 + 4096) * 8));   // + per-block counts of the ordered compaction
+  ENG_CUDA(cudaMalloc(&mp.counters, (16 + 4096) * 8));
+  ENG_CUDA(cudaMalloc(&mp.scan_queue, kScanQueueWords * sizeof(uint32_t)));   // + per-block counts of the ordered compaction
   mp.stats = mp.counters + 8;
   mp.debug = nullptr;
   mp.trace = nullptr;

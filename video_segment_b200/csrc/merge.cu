@@ -920,6 +920,7 @@ constexpr unsigned long long kBlockRoundsLimit = 2048;   // residual lists up to
 // three grid barriers plus several dependent global loads, and a chain needs one round per link).
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanMax = 2048;
+constexpr unsigned long long kGroupScanMin = 1024;   // residuals above this are scanned group-parallel by all CTAs
 constexpr int kScanHashBits = 13;                // 4 * kScanMax slots
 static_assert((1 << kScanHashBits) == 4 * kScanMax, "hash size");
 struct ScanShared;
@@ -968,11 +969,27 @@ __device__ __forceinline__ unsigned short scan_lookup(const ScanShared& C, unsig
   return C.hidx[slot];
 }
 
-// all threads of ONE block; pend_list[0 .. n_pend) ascending positions relative to codes / done_flags
+// A hub "commutes" in a segment when its decision-relevant state (big, flag, constraint id) cannot
+// change there: finalised, or certified frozen for this segment (NodeScratch::frozen == wtag).
+__device__ __forceinline__ bool commuting_hub(const MergeParams& p, int r, int wtag) {
+  const int sz = p.rec[r].sz;
+  if (sz < p.min_region_size) return false;
+  return p.rec[r].fin != 0 || p.hull[r].frozen == wtag;
+}
+
+// all threads of ONE block; pend_list[0 .. n_pend) ascending positions relative to codes / done_flags.
+// commute_tag >= 0: several CTAs scan disjoint groups of regions at the same time; commuting hubs are shared
+// between them, so they only absorb (fixed-point accumulators, folded by the caller behind a barrier) and
+// an edge that would need a hub's exact record defers its whole group (grp_of[i] = group of edge i) to the
+// caller's serial tail: its edges stay pending.  commute_tag < 0: plain exact scan, every root is owned.
 __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, const uint32_t* codes, const uint32_t* pend_list,
-                           const int n_pend, unsigned char* done_flags) {
+                           const int n_pend, unsigned char* done_flags, const int commute_tag, const uint32_t* grp_of,
+                           unsigned long long* deferred_flag) {
   const float edge_w = (float)b * (float)(1.0 / (double)bucket_scale());
+  const int mins = p.min_region_size;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  unsigned char* const ishub = reinterpret_cast<unsigned char*>(C.tru);     // tru / trv are free once the ids are looked up
+  unsigned char* const skip = reinterpret_cast<unsigned char*>(C.trv);      // per edge: left pending (deferred group)
   for (int i = tid; i < 4 * kScanMax; i += nthr) { C.hkey[i] = 0u; C.hidx[i] = 0xFFFFu; }
   if (tid == 0) C.n_roots = 0;
   __syncthreads();
@@ -996,13 +1013,55 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
   for (int j = tid; j < n_roots; j += nthr) {
     C.par[j] = (unsigned short)j;
     scan_store(C.rec, j, load_rec(&p.rec[C.gid[j]]));
+    ishub[j] = (commute_tag >= 0 && commuting_hub(p, C.gid[j], commute_tag)) ? 1 : 0;
   }
+  for (int i = tid; i < n_pend; i += nthr) skip[i] = 0;
   __syncthreads();
   if (tid == 0) {
     auto findl = [&](int x) { int q = C.par[x]; while (q != x) { const int g = C.par[q]; C.par[x] = (unsigned short)g; x = q; q = g; } return x; };
+    uint32_t deferred[16];
+    int n_def = 0;
     for (int i = 0; i < n_pend; ++i) {
+      if (n_def) {
+        bool d = false;
+        for (int k = 0; k < n_def; ++k) d = d || (deferred[k] == grp_of[i]);
+        if (d) { skip[i] = 1; continue; }
+      }
       const int a = findl(C.ea[i]), bq = findl(C.eb[i]);
       if (a == bq) continue;
+      const bool ha = ishub[a] != 0, hb = ishub[bq] != 0;
+      if (ha || hb) {
+        // a shared hub: only outcomes that do not need (or change) its exact record are taken here
+        bool conflict = false;
+        if (ha && hb) {
+          const RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
+          const bool both_con = A.con >= 0 && B.con >= 0;
+          const bool noop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin));
+          conflict = !noop;
+        } else {
+          const int h = ha ? a : bq, x = ha ? bq : a;
+          const RegionRec H = scan_load(C.rec, h), X = scan_load(C.rec, x);
+          if (X.con >= 0) {
+            conflict = !(H.con >= 0 && H.con != X.con);          // different ids: the edge is kept, nothing happens
+          } else if (!((H.fin || X.fin) && X.sz >= mins)) {       // not inert: the hub absorbs X (small side / certified test)
+            C.par[x] = (unsigned short)h;
+            acc_add(p.acc, C.gid[h], X);
+          }
+        }
+        if (conflict) {
+          skip[i] = 1;
+          *deferred_flag = 1ull;
+          // later scans of this CTA must skip the group as well: remember it in global memory (group id = a node id)
+          p.hull[grp_of[i]].claim = -commute_tag - 1;
+          if (n_def < 16) deferred[n_def++] = grp_of[i];
+          else {
+            // cannot track more groups locally: everything left in this batch stays pending and all of its groups are deferred
+            for (int k = i + 1; k < n_pend; ++k) { skip[k] = 1; p.hull[grp_of[k]].claim = -commute_tag - 1; }
+            break;
+          }
+        }
+        continue;
+      }
       RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
       const int r = decide_pair(p, A, B, edge_w);      // rep_1 = root of region_1 (the anchor), as in the reference
       if (r != 2) scan_store(C.rec, a, A);              // survivor, or flags / constraint changed without a merge
@@ -1017,12 +1076,12 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
     while (C.par[x] != x) x = C.par[x];
     const int g = C.gid[j];
     if (x == j) {
-      store_rec(&p.rec[g], scan_load(C.rec, j));
+      if (!ishub[j]) store_rec(&p.rec[g], scan_load(C.rec, j));       // shared hubs are folded by the caller
     } else {
       p.parent[g] = C.gid[x];
     }
   }
-  for (int i = tid; i < n_pend; i += nthr) done_flags[C.epos[i]] = 1;
+  for (int i = tid; i < n_pend; i += nthr) if (!skip[i]) done_flags[C.epos[i]] = 1;
   if (tid == 0) atomicAdd(&p.stats[3], 1ull);
   __syncthreads();
 }
@@ -1596,11 +1655,89 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           }
           bar.sync();
           VSB_PHASE(3);                            // ordered compaction of the pending positions
-          if (!kIsGrid || blockIdx.x == 0) {
+          bool serial_tail = true;
+          if (kIsGrid && n_pend > kGroupScanMin && !(p.dev_flags & 16)) {
+            // ---- group-parallel exact scans: regions joined by pending edges (not through commuting hubs)
+            // form independent groups; every CTA scans the groups hashed to it, in reference order ----
+            uint32_t* const grp = st.buf ? p.live_c : p.live_b;           // the list buffer the compaction did not use
+            uint2* const roots = reinterpret_cast<uint2*>(grp + n_pend + (n_pend & 1ull));
+            if (tid == 0) p.counters[7] = 0ull;
+            for (unsigned long long i = tid; i < n_pend; i += nthr) {
+              int u, v;
+              decode_edge(p, codes[pend_list[i]], u, v);
+              const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+              roots[i] = make_uint2((unsigned)ru, (unsigned)rv);
+              if (ru != rv && !commuting_hub(p, ru, wtag) && !commuting_hub(p, rv, wtag)) cl_union(p.cl, ru, rv);
+            }
+            bar.sync();
+            for (unsigned long long i = tid; i < n_pend; i += nthr) {
+              const uint2 r = roots[i];
+              const bool cu = commuting_hub(p, (int)r.x, wtag), cv = commuting_hub(p, (int)r.y, wtag);
+              // an edge between two commuting hubs has no group: it is left to the serial tail
+              grp[i] = (cu && cv) ? 0xFFFFFFFFu : (uint32_t)cl_find_compress(p.cl, cu ? (int)r.y : (int)r.x);
+              if (cu && cv && r.x != r.y) p.counters[7] = 1ull;
+            }
+            bar.sync();
+            {
+              ScanShared& C = *reinterpret_cast<ScanShared*>(&S);
+              uint32_t* const q_pos = p.scan_queue + (unsigned long long)blockIdx.x * 2ull * kScanMax;   // per-CTA queue of (position, group)
+              uint32_t* const q_grp = q_pos + kScanMax;
+              const int deftag = -wtag - 1;
+              int q_n = 0;
+              for (unsigned long long base = 0; base < n_pend; base += blockDim.x) {
+                const unsigned long long i = base + threadIdx.x;
+                uint32_t g = 0xFFFFFFFFu;
+                bool mine = false;
+                if (i < n_pend) {
+                  g = grp[i];
+                  mine = g != 0xFFFFFFFFu && (g * 2654435761u >> 8) % gridDim.x == blockIdx.x && p.hull[g].claim != deftag;
+                }
+                unsigned total;
+                const unsigned rank = block_rank(S, mine, &total);
+                if (mine) { q_pos[q_n + rank] = pend_list[i]; q_grp[q_n + rank] = g; }
+                q_n += (int)total;
+                __syncthreads();
+                if (q_n + (int)blockDim.x > kScanMax) {
+                  exact_scan(p, C, b, codes, q_pos, q_n, p.done, wtag, q_grp, &p.counters[7]);
+                  q_n = 0;
+                }
+              }
+              if (q_n) exact_scan(p, C, b, codes, q_pos, q_n, p.done, wtag, q_grp, &p.counters[7]);
+            }
+            bar.sync();
+            // fold what the commuting hubs absorbed, group scratch back to idle
+            for (unsigned long long i = tid; i < n_pend; i += nthr) {
+              const uint2 r = roots[i];
+              acc_fold(p, (int)r.x); acc_fold(p, (int)r.y);
+              p.cl[r.x] = (int)r.x; p.cl[r.y] = (int)r.y;
+            }
+            bar.sync();
+            serial_tail = *((volatile unsigned long long*)&p.counters[7]) != 0ull;
+            if (serial_tail) {
+              // deferred groups / hub-hub edges: what is still pending runs through ONE exact scan, in order
+              if (!kIsGrid || blockIdx.x == 0) {
+                unsigned long long m = 0;
+                for (unsigned long long base = 0; base < n_pend; base += blockDim.x) {
+                  const unsigned long long i = base + threadIdx.x;
+                  const bool flag = (i < n_pend) && (p.done[pend_list[i]] == 0);
+                  unsigned total;
+                  const unsigned rank = block_rank(S, flag, &total);
+                  if (flag) grp[m + rank] = pend_list[i];
+                  m += total;
+                  __syncthreads();
+                }
+                for (unsigned long long q0 = 0; q0 < m; q0 += kScanMax)
+                  exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, grp + q0, (int)min((unsigned long long)kScanMax, m - q0), p.done, -1, nullptr, nullptr);
+              }
+              bar.sync();
+            }
+            serial_tail = false;
+          }
+          if (serial_tail && (!kIsGrid || blockIdx.x == 0)) {
             if (n_pend <= (unsigned long long)kScanMax || !(p.dev_flags & 8)) {
               // the pending edges in reference order, kScanMax at a time (each batch reloads the current roots)
               for (unsigned long long q0 = 0; q0 < n_pend; q0 += kScanMax)
-                exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, pend_list + q0, (int)min((unsigned long long)kScanMax, n_pend - q0), p.done);
+                exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, pend_list + q0, (int)min((unsigned long long)kScanMax, n_pend - q0), p.done, -1, nullptr, nullptr);
             } else serial_rounds(p, S, b, codes, pend_list, n_pend, wtag, p.done);
           }
           bar.sync();
