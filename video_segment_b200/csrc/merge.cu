@@ -945,12 +945,13 @@ struct ScanShared {
   unsigned hkey[4 * kScanMax];                      // hash: global root + 1 (0 = empty)
   unsigned short hidx[4 * kScanMax];                // local id of the slot's root
   int n_roots;
+  int hbits;                                        // hash size of the current scan: 4 x its edge count, rounded up to a power of two
 };
 static_assert(sizeof(ScanShared) <= sizeof(SerialShared), "ScanShared overlays SerialShared");
 
 // phase 1 (insert) and phase 2 (lookup, after a block barrier) of the root -> local id hash
 __device__ __forceinline__ void scan_insert(ScanShared& C, unsigned root) {
-  unsigned slot = (root * 2654435761u) >> (32 - kScanHashBits);       // kScanHashBits bits
+  unsigned slot = (root * 2654435761u) >> (32 - C.hbits);
   while (true) {
     const unsigned k = atomicCAS(&C.hkey[slot], 0u, root + 1u);
     if (k == 0u) {
@@ -960,12 +961,12 @@ __device__ __forceinline__ void scan_insert(ScanShared& C, unsigned root) {
       return;
     }
     if (k == root + 1u) return;
-    slot = (slot + 1u) & (4 * kScanMax - 1);
+    slot = (slot + 1u) & ((1u << C.hbits) - 1u);
   }
 }
 __device__ __forceinline__ unsigned short scan_lookup(const ScanShared& C, unsigned root) {
-  unsigned slot = (root * 2654435761u) >> (32 - kScanHashBits);
-  while (C.hkey[slot] != root + 1u) slot = (slot + 1u) & (4 * kScanMax - 1);
+  unsigned slot = (root * 2654435761u) >> (32 - C.hbits);
+  while (C.hkey[slot] != root + 1u) slot = (slot + 1u) & ((1u << C.hbits) - 1u);
   return C.hidx[slot];
 }
 
@@ -990,8 +991,10 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
   const int tid = threadIdx.x, nthr = blockDim.x;
   unsigned char* const ishub = reinterpret_cast<unsigned char*>(C.tru);     // tru / trv are free once the ids are looked up
   unsigned char* const skip = reinterpret_cast<unsigned char*>(C.trv);      // per edge: left pending (deferred group)
-  for (int i = tid; i < 4 * kScanMax; i += nthr) { C.hkey[i] = 0u; C.hidx[i] = 0xFFFFu; }
-  if (tid == 0) C.n_roots = 0;
+  int hbits = 6;
+  while ((1 << hbits) < 4 * n_pend) ++hbits;          // <= kScanHashBits since n_pend <= kScanMax
+  for (int i = tid; i < (1 << hbits); i += nthr) { C.hkey[i] = 0u; C.hidx[i] = 0xFFFFu; }
+  if (tid == 0) { C.n_roots = 0; C.hbits = hbits; }
   __syncthreads();
   for (int i = tid; i < n_pend; i += nthr) {
     const uint32_t pos = pend_list[i];
