@@ -71,6 +71,25 @@ def test_edge_weights_parity(K, shape, l1):
     assert none is None and np.array_equal(sp0.cpu().numpy().transpose(2, 0, 1), sp_ref)
 
 
+@pytest.mark.parametrize("shape", [(24, 128), (37, 68), (17, 192)])
+def test_edge_weights_flat_patches_parity(K, shape):
+    """Identical neighbouring pixels (zero colour distance) take the exact-sqrt slow path of the packed /
+    scalar TMA kernels; widths cover the packed kernel (w % 64 == 0) and the scalar TMA kernel (w % 4 == 0)."""
+    h, w = shape
+    rng = np.random.default_rng(21)
+    a = rng.random((h, w, 3), dtype=np.float32)
+    b = rng.random((h, w, 3), dtype=np.float32)
+    a[3:9, 5:40] = a[3, 5]                      # flat patch inside frame t
+    b[2:12, 20:70] = a[3, 5]                    # and the same colour in frame t-1
+    a[h - 4:, w - 30:] = 0.0
+    b[h - 4:, w - 30:] = 0.0
+    a[10:14, :] *= np.float32(1e-20)            # tiny but non-zero differences (below the fast-path range)
+    sp_ref, tp_ref = ob.spatial_weights(a), ob.temporal_weights(a, b, None)
+    sp, tp = K.edge_build(_dev(a), _dev(b), None, False)
+    assert np.array_equal(sp.cpu().numpy().transpose(2, 0, 1), sp_ref)
+    assert np.array_equal(tp.cpu().numpy().transpose(2, 0, 1), tp_ref)
+
+
 def test_edge_weights_flow_parity(K):
     h, w = 45, 70
     clip = synth_clip(10, w, h, 2)

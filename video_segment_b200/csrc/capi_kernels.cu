@@ -161,8 +161,8 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     mp.counters = (unsigned long long*)dalloc((16 + 4096) * 8);
     mp.scan_queue = (uint32_t*)dalloc(kScanQueueWords * sizeof(uint32_t));
     mp.stats = mp.counters ? mp.counters + 8 : nullptr;
-    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 32) * 8) : nullptr;
-    if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, s);
+    mp.debug = getenv("VSB200_MERGE_DEBUG") ? (unsigned long long*)dalloc((kNumBuckets * 4 + 64) * 8) : nullptr;
+    if (mp.debug) cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 64) * 8, s);
     mp.trace = nullptr;
     unsigned long long* h_trace = nullptr;
     std::atomic<bool> trace_stop{false};
@@ -203,7 +203,7 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
       break;
     }
     if (mp.debug) {
-      std::vector<unsigned long long> dbg(kNumBuckets * 4 + 32);
+      std::vector<unsigned long long> dbg(kNumBuckets * 4 + 64);
       cudaMemcpy(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost);
       FILE* f = fopen(getenv("VSB200_MERGE_DEBUG"), "w");
       if (f) {

@@ -492,13 +492,13 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   mp.live_cap = live_cap_alloc;
   ENG_CUDA(cudaMemsetAsync(mp.stats, 0, 8 * 8, stream));
   const char* dbg_path = getenv("VSB200_MERGE_DEBUG");       // per-bucket profile of every chunk (development tap)
-  if (dbg_path && !mp.debug) ENG_CUDA(cudaMalloc(&mp.debug, (kNumBuckets * 4 + 32) * 8));
-  if (mp.debug) ENG_CUDA(cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 32) * 8, stream));
+  if (dbg_path && !mp.debug) ENG_CUDA(cudaMalloc(&mp.debug, (kNumBuckets * 4 + 64) * 8));
+  if (mp.debug) ENG_CUDA(cudaMemsetAsync(mp.debug, 0, (kNumBuckets * 4 + 64) * 8, stream));
   ENG_RC(launch_merge(mp, stream));
   if (mp.debug && dbg_path) {
     unsigned long long h_scan = 0;
     cudaMemcpyAsync(&h_scan, mp.stats + 3, 8, cudaMemcpyDeviceToHost, stream);
-    std::vector<unsigned long long> dbg(kNumBuckets * 4 + 32);
+    std::vector<unsigned long long> dbg(kNumBuckets * 4 + 64);
     ENG_CUDA(cudaMemcpyAsync(dbg.data(), mp.debug, dbg.size() * 8, cudaMemcpyDeviceToHost, stream));
     ENG_CUDA(cudaStreamSynchronize(stream));
     const std::string path = std::string(dbg_path) + ".chunk" + std::to_string(chunk_id);
@@ -515,6 +515,8 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
               c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7]);
       fprintf(f, "phase ms: raw_prune %.1f certify %.1f ordered_rounds %.1f compaction %.1f hubhub_refresh %.1f exact_scan %.1f serial_mode %.1f; exact scans %llu (%llu edges), serial calls %llu (%llu edges)\n",
               c[12] / 1e6, c[13] / 1e6, c[14] / 1e6, c[15] / 1e6, c[16] / 1e6, c[17] / 1e6, c[18] / 1e6, h_scan, c[19], c[20], c[21]);
+      fprintf(f, "certify passes ms: C1 union %.1f C2 records %.1f C3 hubs %.1f C4 count %.1f C5 apply %.1f C6 fold+reset %.1f\n",
+              c[32] / 1e6, c[33] / 1e6, c[34] / 1e6, c[35] / 1e6, c[36] / 1e6, c[37] / 1e6);
       fprintf(f, "hub_not_frozen reasons: same_id_or_hubs3 %llu con_conflict %llu open_hubs3 %llu bound %llu\n", c[8], c[9], c[10], c[11]);
       fclose(f);
     }

@@ -239,522 +239,11 @@ __device__ __forceinline__ void acc_fold(const MergeParams& p, int root) {
   store_rec(&p.rec[root], R);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Serial window mode.  When the grid-wide rounds stop making progress (a long dependency chain:
-// one region growing edge by edge in reference order) block 0 finishes the chain alone: it keeps
-// the kWin smallest pending edges of the bucket (in reference order) in shared memory and runs
-// the same reservation rounds on them behind __syncthreads, with the reservations in a shared
-// hash table.  A window holds every earlier pending edge of each of its edges, so owning both
-// roots inside the window is again "next edge in reference order" -- exact, ~2 us per round.
-// ---------------------------------------------------------------------------------------------
-constexpr int kWin = 2048;
-constexpr int kHash = 8192;
-
-struct SerialShared {
-  uint32_t code[kWin], pos[kWin], ru[kWin], rv[kWin];
-  unsigned hkey[kHash], hval[kHash];
-  unsigned short htag[kHash];      // run (head index + 1) that scheduled this root as a leaf, 0 = none
-  unsigned short hcnt[kHash];      // window entries touching this root
-  unsigned short su[kWin], sv[kWin];   // hash slots of an entry's two roots
-  unsigned short owner[kWin];      // head index + 1 of the run an entry belongs to, 0 = none
-  unsigned char kind[kWin];        // 0 done, 1 head (owns both roots), 2 owns rv only, 3 owns ru only, 4 owns neither; +8 = leaf item of a run, +16 = duplicate item of a run
-  int run_start[kWin / 2], run_len[kWin / 2], run_hub[kWin / 2];
-  int n_runs, run_next;
-  unsigned warp_cnt[kMergeWarps];
-  int lsz[kWin], lcon[kWin], lfin[kWin];   // leaf records of run items, prefetched by the whole block
-  float ld0[kWin], ld1[kWin], ld2[kWin];
-  int wn, taken, commits;
-  unsigned long long cursor, next_cursor;
-};
-
-__device__ __forceinline__ unsigned hash_slot(unsigned root) { return (root * 2654435761u) >> 19; }   // 13 bits
-__device__ __forceinline__ unsigned hash_min(SerialShared& S, unsigned root, unsigned val) {
-  unsigned slot = hash_slot(root);
-  while (true) {
-    const unsigned k = atomicCAS(&S.hkey[slot], 0u, root + 1u);
-    if (k == 0u || k == root + 1u) {
-      atomicMin(&S.hval[slot], val);
-      // 16-bit counters packed two per word: use a 32-bit atomic on the containing word
-      unsigned* w = reinterpret_cast<unsigned*>(&S.hcnt[slot & ~1u]);
-      atomicAdd(w, (slot & 1u) ? 0x10000u : 1u);
-      return slot;
-    }
-    slot = (slot + 1u) & (kHash - 1);
-  }
-}
-__device__ __forceinline__ unsigned hash_get(const SerialShared& S, unsigned root) {
-  unsigned slot = hash_slot(root);
-  while (true) {
-    const unsigned k = S.hkey[slot];
-    if (k == root + 1u) return S.hval[slot];
-    if (k == 0u) return 0xFFFFFFFFu;
-    slot = (slot + 1u) & (kHash - 1);
-  }
-}
-
-__device__ __forceinline__ int hash_find(const SerialShared& S, unsigned root) {
-  unsigned slot = hash_slot(root);
-  while (true) {
-    const unsigned k = S.hkey[slot];
-    if (k == root + 1u) return (int)slot;
-    if (k == 0u) return -1;
-    slot = (slot + 1u) & (kHash - 1);
-  }
-}
-
-// block-wide exclusive scan of a 0/1 flag over 256 threads; returns rank, total via smem
-__device__ __forceinline__ unsigned block_rank(SerialShared& S, bool flag, unsigned* total) {
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned m = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) S.warp_cnt[wid] = __popc(m);
-  __syncthreads();
-  unsigned base = 0, tot = 0;
-#pragma unroll
-  for (int k = 0; k < kMergeWarps; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
-  __syncthreads();
-  *total = tot;
-  return base + __popc(m & ((1u << lane) - 1u));
-}
-
-// Returns true when the bucket is finished, false when the window became productive again
-// (many commits per round: hand back to the grid-wide rounds).
-// pend[0 .. n_edges) = positions (relative to codes / done_flags) of the segment's pending edges in reference order
-__device__ bool serial_rounds(const MergeParams& p, SerialShared& S, const int b, const uint32_t* codes,
-                              const uint32_t* pend_list, const unsigned long long n_edges, const int wtag, unsigned char* done_flags) {
-  const float inv_scale = (float)(1.0 / (double)bucket_scale());
-  const float edge_w = (float)b * inv_scale;
-  const int mins = p.min_region_size;
-  const int tid = threadIdx.x;
-  if (tid == 0) { S.wn = 0; S.cursor = 0; trace(p, 3, 100); }
-  for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; S.htag[i] = 0; S.hcnt[i] = 0; }
-  __syncthreads();
-  unsigned long long rounds = 0;
-  int productive = 0;
-  long long tmark = clock64();
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define VSB_T(slot) do { if (tid == 0) { const long long t_ = clock64(); tacc[slot] += t_ - tmark; tmark = t_; } } while (0)
-  while (true) {
-    // ---- refill the window with the next pending edges in reference order ----
-    while (true) {
-      const int wn = S.wn;
-      const unsigned long long cur = S.cursor;
-      if (wn >= kWin || cur >= n_edges) break;
-      const unsigned long long idx = cur + tid;
-      uint32_t pos = 0;
-      bool pend = false;
-      if (idx < n_edges) { pos = pend_list[idx]; pend = (done_flags[pos] == 0); }
-      unsigned total;
-      const unsigned rank = block_rank(S, pend, &total);
-      const unsigned room = (unsigned)(kWin - wn);
-      if (tid == 0) S.next_cursor = cur + kMergeThreads;
-      __syncthreads();
-      if (pend) {
-        if (rank < room) { S.code[wn + rank] = codes[pos]; S.pos[wn + rank] = pos; }
-        else if (rank == room) S.next_cursor = idx;      // first pending edge that did not fit
-      }
-      __syncthreads();
-      if (tid == 0) { S.wn = wn + (int)min(total, room); S.cursor = S.next_cursor; S.commits = 0; }
-      __syncthreads();
-    }
-    const int wn = S.wn;
-    if (wn == 0) return true;
-    if (tid == 0) S.commits = 0;
-    VSB_T(0);
-    // ---- A: roots, inert edges, reservations (window index == reference order) ----
-    {
-      constexpr int kU = kWin / kMergeThreads;
-      int us[kU], vs[kU], pu[kU], pv[kU];
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        const int i = tid + q * kMergeThreads;
-        us[q] = -1;
-        if (i < wn) decode_edge(p, S.code[i], us[q], vs[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < kU; ++q) { pu[q] = p.parent[us[q] >= 0 ? us[q] : 0]; pv[q] = p.parent[us[q] >= 0 ? vs[q] : 0]; }   // first hops in flight together
-      RegionRec As[kU], Bs[kU];
-      int rus[kU], rvs[kU];
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        if (us[q] < 0) continue;
-        rus[q] = (pu[q] == us[q]) ? us[q] : uf_find(p.parent, pu[q]);
-        rvs[q] = (pv[q] == vs[q]) ? vs[q] : uf_find(p.parent, pv[q]);
-        if (pu[q] != us[q] && rus[q] != pu[q]) p.parent[us[q]] = rus[q];     // path compression
-        if (pv[q] != vs[q] && rvs[q] != pv[q]) p.parent[vs[q]] = rvs[q];
-      }
-#pragma unroll
-      for (int q = 0; q < kU; ++q) { const bool v_ = us[q] >= 0; As[q] = load_rec(&p.rec[v_ ? rus[q] : 0]); Bs[q] = load_rec(&p.rec[v_ ? rvs[q] : 0]); }
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        if (us[q] < 0) continue;
-        const int i = tid + q * kMergeThreads;
-        const int ru = rus[q], rv = rvs[q];
-        bool drop = (ru == rv);
-        if (!drop) {
-          const RegionRec& A = As[q];
-          const RegionRec& B = Bs[q];
-          const bool both_con = (A.con >= 0 && B.con >= 0);
-          drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
-        }
-        if (drop) {
-          done_flags[S.pos[i]] = 1;
-          S.code[i] = kDone;
-          S.ru[i] = 0xFFFFFFFFu; S.rv[i] = 0xFFFFFFFFu;
-        } else {
-          S.ru[i] = (uint32_t)ru; S.rv[i] = (uint32_t)rv;
-          S.su[i] = (unsigned short)hash_min(S, (unsigned)ru, (unsigned)i);
-          S.sv[i] = (unsigned short)hash_min(S, (unsigned)rv, (unsigned)i);
-        }
-      }
-    }
-    __syncthreads();
-    VSB_T(1);
-    // ---- B1: who owns what ----
-    if (tid == 0) { S.n_runs = 0; S.run_next = 0; }
-    for (int i = tid; i < wn; i += kMergeThreads) {
-      unsigned char k = 0;
-      if (S.code[i] != kDone) {
-        const bool own_u = S.hval[S.su[i]] == (unsigned)i, own_v = S.hval[S.sv[i]] == (unsigned)i;
-        k = (own_u && own_v) ? 1 : own_v ? 2 : own_u ? 3 : 4;
-      }
-      S.kind[i] = k;
-      S.owner[i] = 0;
-    }
-    __syncthreads();
-    // ---- B2: hub runs.  A head i owns both its roots {a, b}.  Walking the window in reference
-    // order after i, every entry that touches a or b is the next edge of the hub a+b provided
-    // its other root x is a fresh leaf it owns (first window entry of x) -> leaf item, or a leaf
-    // already scheduled by this run / the other head root -> duplicate item (internal once the
-    // leaf merged).  The walk stops at the first hub entry that is neither, or at the first
-    // entry that touches a scheduled leaf from outside the hub.  All items then are, in order,
-    // the next edges of the hub in the reference scan and are applied sequentially. ----
-    for (int i = tid; i < wn; i += kMergeThreads) {
-      if (S.kind[i] != 1) continue;
-      const unsigned a = S.ru[i], b = S.rv[i];
-      const unsigned short me = (unsigned short)(i + 1);
-      int items = 0;
-      // both roots touched by this entry only: nothing to walk
-      const int hub_entries = (int)S.hcnt[S.su[i]] + (int)S.hcnt[S.sv[i]] - 2;
-      int seen = 0;
-      for (int j = i + 1; j < wn && seen < hub_entries; ++j) {
-        const unsigned char k = S.kind[j];
-        if (k == 0) continue;
-        const unsigned u = S.ru[j], v = S.rv[j];
-        const bool tu = (u == a || u == b), tv = (v == a || v == b);
-        if (tu && tv) { S.owner[j] = me; S.kind[j] = k | 16; ++items; seen += 2; continue; }
-        if (tu || tv) {
-          ++seen;
-          const int sx = tu ? S.sv[j] : S.su[j];
-          if (S.htag[sx] == me) { S.owner[j] = me; S.kind[j] = k | 16; ++items; continue; }
-          const bool owns_x = tu ? (k == 2) : (k == 3);     // kind 2 owns rv, kind 3 owns ru
-          if (!owns_x) break;
-          S.htag[sx] = me;
-          S.owner[j] = me; S.kind[j] = k | 8; ++items;
-          continue;
-        }
-        // foreign entry: conflict if it touches a leaf this run scheduled
-        if (S.htag[S.su[j]] == me || S.htag[S.sv[j]] == me) break;
-      }
-      if (items == 0) {
-        // isolated head: nobody else touches its two roots this round
-        exec_strict(p, (int)a, (int)b, edge_w, p.stats);
-        done_flags[S.pos[i]] = 1;
-        S.code[i] = kDone;
-        atomicAdd(&S.commits, 1);
-      } else {
-        const int slot = atomicAdd(&S.n_runs, 1);
-        S.run_start[slot] = i; S.run_len[slot] = items; S.run_hub[slot] = 0;
-      }
-    }
-    __syncthreads();
-    VSB_T(2);
-    // leaf records of all run items -> shared memory (one parallel gather instead of a global
-    // load per 32-entry step of the sequential executors)
-    {
-      constexpr int kU = kWin / kMergeThreads;
-      int xs[kU];
-      RegionRec Xs[kU];
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        const int j = tid + q * kMergeThreads;
-        xs[q] = -1;
-        if (j < wn && S.owner[j] != 0 && (S.kind[j] & 8)) {
-          const unsigned short o1 = S.owner[j];
-          const unsigned ha = S.ru[o1 - 1], hb = S.rv[o1 - 1];
-          const bool hub_is_u = (S.ru[j] == ha || S.ru[j] == hb);
-          xs[q] = hub_is_u ? (int)S.rv[j] : (int)S.ru[j];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kU; ++q) Xs[q] = load_rec(&p.rec[xs[q] >= 0 ? xs[q] : 0]);     // unconditional: loads stay in flight together
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        if (xs[q] < 0) continue;
-        const int j = tid + q * kMergeThreads;
-        S.lsz[j] = Xs[q].sz; S.lcon[j] = Xs[q].con; S.lfin[j] = Xs[q].fin;
-        S.ld0[j] = Xs[q].d0; S.ld1[j] = Xs[q].d1; S.ld2[j] = Xs[q].d2;
-      }
-    }
-    __syncthreads();
-    VSB_T(3);
-    // ---- B3: execute runs.  Warps take runs from a shared counter; lanes look at 32 window
-    // slots at a time, prefetch the leaves' records, lane 0 applies the items in order with the
-    // hub record in registers. ----
-    {
-      const unsigned lane = tid & 31;
-      while (true) {
-        int r = 0;
-        if (lane == 0) r = atomicAdd(&S.run_next, 1);
-        r = __shfl_sync(0xffffffffu, r, 0);
-        if (r >= S.n_runs) break;
-        const int i0 = S.run_start[r];
-        const unsigned short me = (unsigned short)(i0 + 1);
-        const unsigned ha = S.ru[i0], hb = S.rv[i0];
-        // head
-        int hub_cur = -1, merged = 0;
-        RegionRec H;
-        H.sz = 0; H.con = -1; H.d0 = H.d1 = H.d2 = 0.f; H.fin = 0; H.pad0 = H.pad1 = 0;
-        if (lane == 0) {
-          RegionRec A = load_rec(&p.rec[(int)ha]), B = load_rec(&p.rec[(int)hb]);
-          const int res = decide_pair(p, A, B, edge_w);
-          if (res == 1) { p.parent[(int)hb] = (int)ha; hub_cur = (int)ha; H = A; merged = 1; }
-          else if (res == 2) { p.parent[(int)ha] = (int)hb; hub_cur = (int)hb; H = B; merged = 1; }
-          else { store_rec(&p.rec[(int)ha], A); store_rec(&p.rec[(int)hb], B); }
-          done_flags[S.pos[i0]] = 1;
-          S.code[i0] = kDone;
-        }
-        merged = __shfl_sync(0xffffffffu, merged, 0);
-        int committed = 1;
-        if (merged) {
-          int remaining = S.run_len[r];
-          for (int base = i0 + 1; base < wn && remaining > 0; base += 32) {
-            const int j = base + (int)lane;
-            const bool mine = (j < wn) && (S.owner[j] == me);
-            const unsigned mask = __ballot_sync(0xffffffffu, mine);
-            if (mask == 0u) continue;
-            remaining -= __popc(mask);
-            const unsigned char kj = mine ? S.kind[j] : 0;
-            const bool is_leaf = mine && (kj & 8);
-            // leaf items: x = the root that is not the hub side
-            int x = -1;
-            bool hub_is_u = false;
-            RegionRec X;
-            X.sz = 0; X.con = -1; X.d0 = X.d1 = X.d2 = 0.f; X.fin = 0; X.pad0 = X.pad1 = 0;
-            if (is_leaf) {
-              hub_is_u = (S.ru[j] == ha || S.ru[j] == hb);
-              x = hub_is_u ? (int)S.rv[j] : (int)S.ru[j];
-              X.sz = S.lsz[j]; X.con = S.lcon[j]; X.fin = S.lfin[j]; X.d0 = S.ld0[j]; X.d1 = S.ld1[j]; X.d2 = S.ld2[j];
-            }
-            // ---- certified fast path: every leaf of this chunk certainly merges into the hub
-            // (un-finalised, unconstrained hub that outweighs each leaf; gate distance plus the
-            // worst-case drift of the hub mean inside the chunk stays below the threshold).  Then
-            // only the running mean is sequential: m <- fa_k * leaf_k + fb_k * m, same float ops
-            // and order as MergeDescriptor; duplicates become internal edges. ----
-            RegionRec Hb;
-            Hb.sz = __shfl_sync(0xffffffffu, H.sz, 0); Hb.con = __shfl_sync(0xffffffffu, H.con, 0);
-            Hb.d0 = __shfl_sync(0xffffffffu, H.d0, 0); Hb.d1 = __shfl_sync(0xffffffffu, H.d1, 0);
-            Hb.d2 = __shfl_sync(0xffffffffu, H.d2, 0); Hb.fin = __shfl_sync(0xffffffffu, H.fin, 0);
-            Hb.pad0 = Hb.pad1 = 0;
-            const int hub_id = __shfl_sync(0xffffffffu, hub_cur, 0);
-            const float dk = is_leaf ? raw_dist(Hb, X) : 0.f;
-            const int my_sz = is_leaf ? X.sz : 0;
-            float psd = (float)my_sz * dk;
-            int psz = my_sz;
-            for (int o = 1; o < 32; o <<= 1) {
-              const float t1 = __shfl_up_sync(0xffffffffu, psd, o);
-              const int t2 = __shfl_up_sync(0xffffffffu, psz, o);
-              if ((int)lane >= o) { psd += t1; psz += t2; }
-            }
-            const int sz_before = Hb.sz + psz - my_sz;
-            const float drift = (psd - (float)my_sz * dk) / (float)Hb.sz;
-            const float thr = (edge_w < p.force_merge_weight) ? 0.2f : 0.05f;
-            bool ok = true;
-            if (is_leaf) {
-              ok = (Hb.con < 0) && (Hb.fin == 0) && (X.con < 0) && (X.sz < Hb.sz);
-              if (ok) {
-                if (X.fin) ok = (X.sz < mins) || (sz_before < mins);
-                else ok = (dk + drift * 1.0001f + 2e-5f) < thr;
-              }
-            }
-            // duplicates are internal only if their leaf merged: in the fast path every leaf of
-            // this and of earlier chunks merged (tracked by all_merged)
-            if (__all_sync(0xffffffffu, ok) && __shfl_sync(0xffffffffu, merged, 0) == 1) {
-              const float denom = 1.0f / (float)(my_sz + sz_before);
-              const float fa = (float)my_sz * denom;
-              const float fb = (float)sz_before * denom;
-              const float c0 = fa * X.d0, c1 = fa * X.d1, c2 = fa * X.d2;
-              float m0 = Hb.d0, m1 = Hb.d1, m2 = Hb.d2;
-              unsigned lm = __ballot_sync(0xffffffffu, is_leaf);
-              while (lm) {
-                const int k = __ffs(lm) - 1;
-                lm &= lm - 1;
-                const float fbk = __shfl_sync(0xffffffffu, fb, k);
-                const float a0 = __shfl_sync(0xffffffffu, c0, k), a1 = __shfl_sync(0xffffffffu, c1, k), a2 = __shfl_sync(0xffffffffu, c2, k);
-                m0 = a0 + fbk * m0;
-                m1 = a1 + fbk * m1;
-                m2 = a2 + fbk * m2;
-              }
-              if (mine) {
-                if (is_leaf) p.parent[x] = hub_id;
-                done_flags[S.pos[j]] = 1;
-                S.code[j] = kDone;
-              }
-              const int tot_sz = __shfl_sync(0xffffffffu, psz, 31);
-              if (lane == 0) { H.d0 = m0; H.d1 = m1; H.d2 = m2; H.sz = Hb.sz + tot_sz; }
-              committed += __popc(mask);
-              continue;
-            }
-            // ---- general path: lane 0 applies the chunk's items one by one.  merged == 2 from
-            // here on: some leaf may have stayed separate, so duplicates are re-examined. ----
-            unsigned m2 = mask;
-            while (m2) {
-              const int k = __ffs(m2) - 1;
-              m2 &= m2 - 1;
-              const int jk = base + k;
-              const int leafk = __shfl_sync(0xffffffffu, (int)is_leaf, k);
-              const int xk = __shfl_sync(0xffffffffu, x, k);
-              const int hu = __shfl_sync(0xffffffffu, (int)hub_is_u, k);
-              RegionRec L;
-              L.sz = __shfl_sync(0xffffffffu, X.sz, k); L.con = __shfl_sync(0xffffffffu, X.con, k);
-              L.d0 = __shfl_sync(0xffffffffu, X.d0, k); L.d1 = __shfl_sync(0xffffffffu, X.d1, k);
-              L.d2 = __shfl_sync(0xffffffffu, X.d2, k); L.fin = __shfl_sync(0xffffffffu, X.fin, k);
-              L.pad0 = 0; L.pad1 = 0;
-              if (lane == 0) {
-                int other = xk;
-                bool hub_first = hu != 0;
-                if (!leafk) {
-                  // duplicate: the other root is a scheduled leaf or the second head root; it is
-                  // internal iff that root now belongs to the hub
-                  const unsigned uu = S.ru[jk], vv = S.rv[jk];
-                  const bool tu = (uu == ha || uu == hb);
-                  const bool tv = (vv == ha || vv == hb);
-                  other = (tu && tv) ? -1 : (int)(tu ? vv : uu);
-                  hub_first = tu;
-                  if (other >= 0) {
-                    const int ro = uf_find(p.parent, other);
-                    if (ro == hub_cur) other = -1;
-                    else { other = ro; L = load_rec(&p.rec[ro]); }
-                  }
-                }
-                if (other >= 0) {
-                  int res;
-                  if (hub_first) { res = decide_pair(p, H, L, edge_w); }
-                  else { res = decide_pair(p, L, H, edge_w); res = (res == 1) ? 2 : (res == 2) ? 1 : 0; }
-                  // res: 1 = hub record survives, 2 = other record survives, 0 = no merge
-                  if (res == 1) { p.parent[other] = hub_cur; }
-                  else if (res == 2) { p.parent[hub_cur] = other; hub_cur = other; H = L; }
-                  else { store_rec(&p.rec[other], L); }
-                }
-                done_flags[S.pos[jk]] = 1;
-                S.code[jk] = kDone;
-                merged = 2;
-              }
-            }
-            committed += __popc(mask);
-          }
-        }
-        if (lane == 0) {
-          if (hub_cur >= 0) store_rec(&p.rec[hub_cur], H);
-          atomicAdd(&S.commits, committed);
-        }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    VSB_T(4);
-    // unclaimed single-owner entries: absorption by a finalised region of >= min size (unordered)
-    {
-      constexpr int kU = kWin / kMergeThreads;
-      bool act[kU];
-      RegionRec As[kU], Bs[kU];
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        const int i = tid + q * kMergeThreads;
-        act[q] = false;
-        if (i < wn) {
-          const unsigned char k = S.kind[i];
-          act[q] = (k == 2 || k == 3) && S.owner[i] == 0 && S.code[i] != kDone;
-        }
-        As[q] = load_rec(&p.rec[act[q] ? (int)S.ru[i] : 0]); Bs[q] = load_rec(&p.rec[act[q] ? (int)S.rv[i] : 0]);
-      }
-#pragma unroll
-      for (int q = 0; q < kU; ++q) {
-        if (!act[q]) continue;
-        const int i = tid + q * kMergeThreads;
-        const unsigned char k = S.kind[i];
-        const int ru = (int)S.ru[i], rv = (int)S.rv[i];
-        const RegionRec& A = As[q];
-        const RegionRec& B = Bs[q];
-        bool done = false;
-        // the other side is a hub whose decision-relevant state cannot change in this window (see run_bucket)
-        // (records were loaded before this round's runs: a hub merged away by a run is skipped until the next round)
-        if (k == 2 && B.con < 0 && A.sz >= mins && B.sz < mins && p.parent[ru] == ru && p.parent[rv] == rv && (A.fin || p.hull[ru].frozen == wtag)) { p.parent[rv] = ru; acc_add(p.acc, ru, B); done = true; }
-        else if (k == 3 && A.con < 0 && B.sz >= mins && A.sz < mins && p.parent[ru] == ru && p.parent[rv] == rv && (B.fin || p.hull[rv].frozen == wtag)) { p.parent[ru] = rv; acc_add(p.acc, rv, A); done = true; }
-        if (done) {
-          done_flags[S.pos[i]] = 1;
-          S.code[i] = kDone;
-          atomicAdd(&S.commits, 1);
-        }
-      }
-    }
-    __syncthreads();
-    VSB_T(5);
-    // ---- C: fold bulk contributions, clear the hash, compact the window (stable) ----
-    for (int i = tid; i < wn; i += kMergeThreads) {
-      if (S.ru[i] == 0xFFFFFFFFu) continue;
-      acc_fold(p, (int)S.ru[i]);
-      acc_fold(p, (int)S.rv[i]);
-    }
-    for (int i = tid; i < kHash; i += kMergeThreads) { S.hkey[i] = 0u; S.hval[i] = 0xFFFFFFFFu; S.htag[i] = 0; S.hcnt[i] = 0; }
-    // stable compaction: each thread owns kPer consecutive window entries
-    constexpr int kPer = kWin / kMergeThreads;
-    uint32_t cc[kPer], pp[kPer];
-    unsigned keep = 0;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int i = tid * kPer + q;
-      cc[q] = kDone; pp[q] = 0;
-      if (i < wn) { cc[q] = S.code[i]; pp[q] = S.pos[i]; }
-      keep += (cc[q] != kDone) ? 1u : 0u;
-    }
-    // block exclusive scan of keep counts (0..kPer)
-    unsigned inc = keep;
-    {
-      const unsigned lane = tid & 31, wid = tid >> 5;
-      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-      if (lane == 31) S.warp_cnt[wid] = inc;
-      __syncthreads();
-      unsigned base = 0, tot = 0;
-#pragma unroll
-      for (int k = 0; k < kMergeWarps; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
-      inc = base + inc - keep;        // exclusive
-      const int commits_now = S.commits;
-      __syncthreads();
-      unsigned d = inc;
-#pragma unroll
-      for (int q = 0; q < kPer; ++q)
-        if (cc[q] != kDone) { S.code[d] = cc[q]; S.pos[d] = pp[q]; ++d; }
-      if (tid == 0) S.wn = (int)tot;
-      __syncthreads();
-      productive = (commits_now * 4 >= kWin) ? productive + 1 : 0;
-    }
-    VSB_T(6);
-    if (tid == 0 && p.debug && (rounds & 63ull) == 63ull) { for (int q = 0; q < 7; ++q) { atomicAdd(&p.debug[kNumBuckets * 4 + q], (unsigned long long)tacc[q]); tacc[q] = 0; } }
-    ++rounds;
-    if (tid == 0 && (rounds & 255ull) == 0) { trace(p, 4, rounds); trace(p, 5, (unsigned long long)S.wn); trace(p, 6, S.cursor); }
-    if (tid == 0 && (rounds & 1023ull) == 0) atomicAdd(&p.stats[0], 1024ull);
-    if (rounds > (1ull << 24)) {        // watchdog: cannot happen (every round retires >= 1 edge)
-      if (tid == 0) { printf("vsb200 merge: serial watchdog bucket %d wn %d cursor %llu n %llu\n", b, S.wn, S.cursor, n_edges); p.stats[7] = 1ull; }
-      return true;
-    }
-    // productive again? (more than a quarter of the window committed for several rounds)
-    (void)productive;   // hub runs retire most of a window per round; the grid rounds cannot do better on a chain
-    if (S.wn == 0 && S.cursor >= n_edges) {
-      if (tid == 0) atomicAdd(&p.stats[0], rounds & 1023ull);
-      return true;
-    }
-  }
-}
+// Shared memory of a CTA: the staging area of the exact scans plus per-warp counters of the
+// block-wide compactions.
+struct ScanShared;
+struct MergeShared;
+__device__ __forceinline__ unsigned block_rank(MergeShared& S, bool flag, unsigned* total);
 
 // ---------------------------------------------------------------------------------------------
 // Window certification.  The pending edges of a bucket are processed in consecutive position
@@ -947,7 +436,24 @@ struct ScanShared {
   int n_roots;
   int hbits;                                        // hash size of the current scan: 4 x its edge count, rounded up to a power of two
 };
-static_assert(sizeof(ScanShared) <= sizeof(SerialShared), "ScanShared overlays SerialShared");
+struct MergeShared {
+  ScanShared scan;
+  unsigned warp_cnt[kMergeWarps];
+};
+
+// block-wide exclusive scan of a 0/1 flag; returns the rank of the calling thread, total via *total
+__device__ __forceinline__ unsigned block_rank(MergeShared& S, bool flag, unsigned* total) {
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) S.warp_cnt[wid] = __popc(m);
+  __syncthreads();
+  unsigned base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < kMergeWarps; ++k) { const unsigned c = S.warp_cnt[k]; if (k < (int)wid) base += c; tot += c; }
+  __syncthreads();
+  *total = tot;
+  return base + __popc(m & ((1u << lane) - 1u));
+}
 
 // phase 1 (insert) and phase 2 (lookup, after a block barrier) of the root -> local id hash
 __device__ __forceinline__ void scan_insert(ScanShared& C, unsigned root) {
@@ -1205,10 +711,11 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
 //           [4] first hub-hub position of the window, [5] uncertified edge count, [6] window tag
 // live entry = 4 words: code, ru, rv, position in the window
 // development tap: wall time per phase (global thread 0), added to debug[kNumBuckets * 4 + 20 + slot]
+#define VSB_CPASS(slot) do { if (p.debug && tid == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.debug[kNumBuckets * 4 + 40 + (slot)] += t_ - t_cpass; t_cpass = t_; } } while (0)
 #define VSB_PHASE(slot) do { if (p.debug && tid == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.debug[kNumBuckets * 4 + 20 + (slot)] += t_ - t_phase; t_phase = t_; } } while (0)
 
 template <class Bar, bool kIsGrid>
-__device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, const unsigned tid, const unsigned nthr,
+__device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const unsigned tid, const unsigned nthr,
                            const int b, const uint32_t* bucket_codes, const unsigned long long bucket_edges) {
   const float inv_scale = (float)(1.0 / (double)bucket_scale());   // segmentation_graph.h:348
   const float edge_w = (float)b * inv_scale;
@@ -1225,7 +732,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
   unsigned long long raw = min(bucket_edges, kWindowTarget);
   unsigned long long guard = 0;
   uint32_t* const master = p.live_a;            // live list of the window (code, ru, rv, position)
-  unsigned long long t_phase = 0;
+  unsigned long long t_phase = 0, t_cpass = 0;
   if (p.debug && tid == 0 && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_phase));
   const unsigned lane = threadIdx.x & 31u;
   while (w0 < bucket_edges) {
@@ -1353,6 +860,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         ++wtag;
         if (tid == 0) { p.counters[5] = 0ull; p.counters[7] = 0ull; }
         bar.sync();
+        if (p.debug && tid == 0 && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cpass));
 #define VSB_IN_SEG(e) (!p.done[(e).w])
         // ---- C1: sub-clusters of small atoms ----
         {
@@ -1368,6 +876,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           if (lane == 0 && mine) atomicAdd(&p.counters[7], mine);
         }
         bar.sync();
+        VSB_CPASS(0);
         if (*((volatile unsigned long long*)&p.counters[7]) == 0ull) break;      // nothing live in this segment
         have_live = true;
         // ---- C2: sub-cluster records (once per atom) and hub adjacency.  Atoms of one sub-cluster
@@ -1430,6 +939,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           }
         }
         bar.sync();
+        VSB_CPASS(1);
         // ---- C3: what every hub may absorb in this segment (once per atom and hub) ----
         for (unsigned long long i0 = seg_lo + (tid - lane); i0 < seg_hi; i0 += nthr) {
           const unsigned long long i = i0 + lane;
@@ -1513,6 +1023,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           }
         }
         bar.sync();
+        VSB_CPASS(2);
         // ---- C4: count the edges the certificates do not cover ----
         {
           unsigned long long mine = 0;
@@ -1540,6 +1051,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           if (lane == 0 && mine) atomicAdd(&p.counters[5], mine);
         }
         bar.sync();
+        VSB_CPASS(3);
         const unsigned long long n_unc = *((volatile unsigned long long*)&p.counters[5]);
         const bool split = (n_unc > kResidualSplit && seg_hi - seg_lo > kSegmentMin);
         // ---- C5: apply the certified merges (skipped when the segment is halved) ----
@@ -1577,6 +1089,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
           }
         }
         bar.sync();
+        VSB_CPASS(4);
         // ---- C6: fold the bulk contributions, scratch back to idle ----
         for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
           const uint4 e = reinterpret_cast<const uint4*>(master)[i];
@@ -1593,6 +1106,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
         }
         if (tid == 0) { atomicAdd(&p.stats[5], 1ull); if (!split) atomicAdd(&p.stats[6], n_unc); }
         bar.sync();
+        VSB_CPASS(5);
         if (!split) { unc_sum += n_unc; break; }
         any_split = true;
         {
@@ -1682,7 +1196,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
             }
             bar.sync();
             {
-              ScanShared& C = *reinterpret_cast<ScanShared*>(&S);
+              ScanShared& C = S.scan;
               uint32_t* const q_pos = p.scan_queue + (unsigned long long)blockIdx.x * 2ull * kScanMax;   // per-CTA queue of (position, group)
               uint32_t* const q_grp = q_pos + kScanMax;
               const int deftag = -wtag - 1;
@@ -1730,18 +1244,16 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
                   __syncthreads();
                 }
                 for (unsigned long long q0 = 0; q0 < m; q0 += kScanMax)
-                  exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, grp + q0, (int)min((unsigned long long)kScanMax, m - q0), p.done, -1, nullptr, nullptr);
+                  exact_scan(p, S.scan, b, codes, grp + q0, (int)min((unsigned long long)kScanMax, m - q0), p.done, -1, nullptr, nullptr);
               }
               bar.sync();
             }
             serial_tail = false;
           }
           if (serial_tail && (!kIsGrid || blockIdx.x == 0)) {
-            if (n_pend <= (unsigned long long)kScanMax || !(p.dev_flags & 8)) {
-              // the pending edges in reference order, kScanMax at a time (each batch reloads the current roots)
-              for (unsigned long long q0 = 0; q0 < n_pend; q0 += kScanMax)
-                exact_scan(p, *reinterpret_cast<ScanShared*>(&S), b, codes, pend_list + q0, (int)min((unsigned long long)kScanMax, n_pend - q0), p.done, -1, nullptr, nullptr);
-            } else serial_rounds(p, S, b, codes, pend_list, n_pend, wtag, p.done);
+            // the pending edges in reference order, kScanMax at a time (each batch reloads the current roots)
+            for (unsigned long long q0 = 0; q0 < n_pend; q0 += kScanMax)
+              exact_scan(p, S.scan, b, codes, pend_list + q0, (int)min((unsigned long long)kScanMax, n_pend - q0), p.done, -1, nullptr, nullptr);
           }
           bar.sync();
           if (p.debug && tid == 0 && blockIdx.x == 0) {
@@ -1812,7 +1324,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, SerialShared& S, cons
 
 __global__ void __launch_bounds__(kMergeThreads) merge_kernel(MergeParams p) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
-  SerialShared& S = *reinterpret_cast<SerialShared*>(merge_smem);
+  MergeShared& S = *reinterpret_cast<MergeShared*>(merge_smem);
   GridBar gbar{cg::this_grid()};
   BlockBar bbar;
   const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1894,7 +1406,7 @@ int launch_merge(const MergeParams& p_in, cudaStream_t s) {
   int dev = 0, sms = 0, per_sm = 0;
   VSB_CUDA_OK(cudaGetDevice(&dev));
   VSB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t smem = sizeof(SerialShared);
+  const size_t smem = sizeof(MergeShared);
   VSB_CUDA_OK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   VSB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_kernel, kMergeThreads, smem));
   if (per_sm < 1) { set_error("merge kernel does not fit on an SM"); return 3; }
