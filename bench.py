@@ -178,13 +178,17 @@ def main():
     halo = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
     halo_in = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
 
-    def seam_exchange(unit):
-        """C1: overlap id maps to the successor group; C2: all-gather of the region-id counts (shard.py)."""
+    def seam_exchange(unit, first_map):
+        """C1: overlap id maps to the successor group; C2: all-gather of the region-id counts; then the
+        parallel-seam relabel of this group's ids by max-overlap voting in the shared frame (shard.py)."""
         if world == 1:
             return
-        from video_segment_b200.shard import seam_exchange as _seam
-        max_id = unit.export_halo(halo[0].data_ptr(), halo[1].data_ptr())
-        _seam(halo, halo_in, max_id, rank, world)
+        from video_segment_b200.shard import relabel_table, seam_exchange as _seam, seam_vote
+        max_id = unit.export_halo(halo[0].data_ptr(), halo[1].data_ptr())[0]
+        got, offsets = _seam(halo, halo_in, max_id, rank, world)
+        if got is not None and first_map is not None:
+            s_ids, p_ids, _ = seam_vote(got[1], first_map)
+            relabel_table(s_ids, p_ids, max_id + 1, offsets[rank]).cpu()      # the table a writer would apply
 
     def run_leg(device_resident):
         unit = DenseSegmentationUnit(device=local_rank)
@@ -200,9 +204,15 @@ def main():
                 return unit.process_device_frame(dev_frames[i].data_ptr(), w * 3)
             return unit.process_frame(pinned[i].numpy())
         out_frames = 0
+        first_map = None             # this group's own segmentation of its first frame (shared with the predecessor)
         # warm-up: W chunks (the first one takes 20 frames)
         while out_frames < FRAMES_PER_STEP * W:
-            out_frames += len(push_next())
+            res = push_next()
+            if res and first_map is None and world > 1:
+                from video_segment_b200.unit import id_map_from_result
+                first_map = torch.from_numpy(id_map_from_result(res[0])).cuda()
+            out_frames += len(res)
+        seam_exchange(unit, first_map)   # warm-up of the exchange too (NCCL opens its peer channels on first use)
         st0, io0 = unit.stats(), unit.io_stats()
         sampler = ClockSampler(local_rank)
         barrier()
@@ -213,7 +223,7 @@ def main():
         timed = 0
         while timed < FRAMES_PER_STEP * K:
             timed += len(push_next())
-        seam_exchange(unit)
+        seam_exchange(unit, first_map)
         torch.cuda.synchronize()
         e1.record()
         barrier()
@@ -262,7 +272,7 @@ def main():
                 "h2d_bytes_per_step": leg_e2e["io"]["h2d_bytes"] / K, "d2h_bytes_per_step": leg_e2e["io"]["d2h_bytes"] / K},
         "gpu_launches": int(leg_dev["stats"]["kernel_launches"]),
         "clocks": leg_dev["clocks"],
-        "roofline": {"bound": "hbm", "kernel": "edge_build_tma_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "edge_build_tma_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": edge_build_bytes(w, h), "ms_per_launch": edge_ms, "launches_timed": int(io["edge_launches"])},
         "stage_ms_per_step": {k2: v / K for k2, v in leg_dev["stats"].items() if k2.endswith("_ms")},

@@ -111,14 +111,20 @@ void vsb200_dense_set_profiling(vsb200_dense*, int time_edge_kernel);
 void vsb200_dense_io_stats(vsb200_dense*, double out[4]);
 void vsb200_dense_destroy(vsb200_dense*);
 
-/* Multi-GPU seam: region-id maps of the two overlap frames a group
- * holds right after a chunk boundary (overlap_segmentations_, dense_segmentation.cpp:300-315),
- * copied into caller-provided DEVICE buffers (int32 [h*w] each) so the caller can
- * ncclSend/ncclRecv them without host staging, plus the group's max region id (C2). */
+/* Multi-GPU seam.  export_halo: region-id maps of the two overlap
+ * frames a group holds right after a chunk boundary (overlap_segmentations_,
+ * dense_segmentation.cpp:300-315), copied into caller-provided DEVICE buffers (int32 [h*w] each)
+ * so the caller can ncclSend/ncclRecv them without host staging, plus the chain state
+ * [0] max region id (max_region_id_, :360-365) [1] id of the chunk the maps constrain
+ * [2] frames output so far.
+ * import_halo: the successor's side.  Called on a fresh handle before its first push, it puts the
+ * engine into the predecessor's post-boundary state; the first push must then be the frame of
+ * dev_id_map_last (the predecessor's last pushed frame).  Results continue exactly as if one
+ * handle had processed the whole sequence (pipelined seam: exact semantics). */
 int vsb200_dense_export_halo(vsb200_dense*, int32_t* dev_id_map_prev_out, int32_t* dev_id_map_last_out,
-                             int32_t* max_region_id);
+                             int32_t chain_state[3]);
 int vsb200_dense_import_halo(vsb200_dense*, const int32_t* dev_id_map_prev,
-                             const int32_t* dev_id_map_last, int32_t max_region_id);
+                             const int32_t* dev_id_map_last, const int32_t chain_state[3]);
 
 /* ---- kernel-level entry points (device pointers; used by the parity tests, bench.py and
  *      the DenseSegGraphInterface adapter).  stream is a cudaStream_t (NULL = default). ---- */

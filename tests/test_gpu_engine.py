@@ -186,6 +186,81 @@ def test_padded_row_stride_matches_contiguous(real_clip):
         assert np.array_equal(a["id_map"], b["id_map"])
 
 
+def _seam_split_run(clip, flows, cut):
+    """Group 0 = frames [0, cut] on one handle, group 1 = frames [cut, T) on a fresh handle seeded through
+    export_halo / import_halo (pipelined seam); cut + 1 pushes must end exactly on a chunk boundary."""
+    import torch
+    from video_segment_b200.unit import DenseSegmentationUnit
+    h, w = clip[0].shape[:2]
+    fl = (lambda i: None) if flows is None else (lambda i: flows[i])
+    a = DenseSegmentationUnit(want_id_maps=True)
+    assert a.open_streams(w, h, flow_stream_present=flows is not None)
+    out = []
+    for i in range(cut + 1):
+        out += a.process_frame(clip[i], fl(i), pts=i)
+    assert len(out) == cut                                   # the boundary fired on the last push
+    halo = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
+    state = a.export_halo(halo[0].data_ptr(), halo[1].data_ptr())
+    a.close()                                                # group 0 never flushes: frame `cut` belongs to group 1
+    b = DenseSegmentationUnit(want_id_maps=True)
+    assert b.open_streams(w, h, flow_stream_present=flows is not None)
+    b.import_halo(halo[0].data_ptr(), halo[1].data_ptr(), state)
+    for i in range(cut, len(clip)):
+        out += b.process_frame(clip[i], fl(i), pts=i)
+    out += b.post_process()
+    b.close()
+    return out, state
+
+
+def _assert_same_results(got, ref):
+    assert len(got) == len(ref)
+    for t, (g, r) in enumerate(zip(got, ref)):
+        for k in ("width", "height", "chunk_id", "chunk_size", "overlap_start", "hierarchy_frame_idx", "connectedness", "pts"):
+            assert g[k] == r[k], (t, k, g[k], r[k])
+        for k in ("region_id", "interval_offset", "intervals", "shape_moments", "id_map"):
+            assert np.array_equal(g[k], r[k]), (t, k)
+        for k in ("compound", "neighbor_offset", "neighbor_id"):
+            if k in r and r[k] is not None:
+                assert np.array_equal(g[k], r[k]), (t, k)
+
+
+def test_seam_import_halo_continues_the_chain_exactly(real_clip):
+    clip = np.concatenate([real_clip, real_clip[::-1]])          # 48 frames -> chunks of 19 + 19 + 10 output frames
+    ref, _, _ = _run_gpu(clip)
+    got, state = _seam_split_run(clip, None, 19)
+    assert state[1] == 1 and state[2] == 19 and state[0] > 0
+    _assert_same_results(got, ref)
+    # second seam position: after two chunks
+    got2, state2 = _seam_split_run(clip, None, 38)
+    assert state2[1] == 2 and state2[2] == 38
+    _assert_same_results(got2, ref)
+
+
+def test_seam_import_halo_with_flow():
+    pairs = list(synth_flow(21, 160, 120, 27))
+    clip = [p[0] for p in pairs]
+    flows = [p[1] for p in pairs]
+    ref, _, _ = _run_gpu(clip, flows)
+    got, _ = _seam_split_run(clip, flows, 19)
+    _assert_same_results(got, ref)
+
+
+def test_seam_import_halo_errors():
+    import torch
+    from video_segment_b200.unit import DenseSegmentationUnit
+    u = DenseSegmentationUnit()
+    assert u.open_streams(64, 48)
+    halo = torch.zeros((2, 48, 64), dtype=torch.int32, device="cuda")
+    with pytest.raises(RuntimeError):
+        u.export_halo(halo[0].data_ptr(), halo[1].data_ptr())         # no chunk boundary yet
+    with pytest.raises(RuntimeError):
+        u.import_halo(halo[0].data_ptr(), halo[1].data_ptr(), [5, 0, 0])   # chunk id of a constrained chunk is >= 1
+    u.process_frame(np.zeros((48, 64, 3), np.uint8))
+    with pytest.raises(RuntimeError):
+        u.import_halo(halo[0].data_ptr(), halo[1].data_ptr(), [5, 1, 19])  # must precede the first push
+    u.close()
+
+
 def test_error_behaviour():
     from video_segment_b200.unit import DenseSegmentationOptions, DenseSegmentationUnit
     u = DenseSegmentationUnit()

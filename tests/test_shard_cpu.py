@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from video_segment_b200.shard import group_range, id_offsets, seam_exchange
+from video_segment_b200.shard import seam_vote, relabel_table, group_range, id_offsets, seam_exchange
 
 
 def test_group_ranges_cover_the_video_with_one_overlap_frame():
@@ -62,3 +62,23 @@ def test_seam_exchange_gloo(world):
             assert got is None
         else:
             assert np.all(got[0] == r) and np.all(got[1] == r + 100)       # the predecessor's two overlap maps
+
+
+def test_seam_vote_max_overlap_and_ties():
+    pred = torch.tensor([[7, 7, 7, 9], [7, 8, 8, 9], [3, 3, 8, 9]], dtype=torch.int32)
+    succ = torch.tensor([[0, 0, 0, 1], [0, 2, 2, 1], [4, 4, 2, -1]], dtype=torch.int32)
+    s, p, c = seam_vote(pred, succ)
+    assert s.tolist() == [0, 1, 2, 4] and p.tolist() == [7, 9, 8, 3] and c.tolist() == [4, 2, 3, 2]
+    # a successor region split evenly between two predecessor regions goes to the smaller id
+    s, p, c = seam_vote(torch.tensor([[5, 5, 2, 2]], dtype=torch.int32), torch.tensor([[1, 1, 1, 1]], dtype=torch.int32))
+    assert s.tolist() == [1] and p.tolist() == [2] and c.tolist() == [2]
+    tab = relabel_table(torch.tensor([0, 1, 2, 4]), torch.tensor([7, 9, 8, 3]), 6, 100)
+    assert tab.tolist() == [7, 9, 8, 103, 3, 105]
+    # identical partitions under a permutation are recovered exactly
+    g = torch.Generator().manual_seed(1)
+    a = torch.randint(0, 50, (40, 60), generator=g, dtype=torch.int32)
+    perm = torch.randperm(50, generator=g).to(torch.int32)
+    s, p, c = seam_vote(a, perm[a.long()])
+    assert torch.equal(perm[p.long()].long(), s)
+    e = seam_vote(torch.full((2, 2), -1, dtype=torch.int32), torch.zeros((2, 2), dtype=torch.int32))
+    assert all(t.numel() == 0 for t in e)

@@ -86,7 +86,7 @@ def lib() -> C.CDLL:
         "vsb200_dense_stats": ([vp, C.POINTER(C.c_double)], None),
         "vsb200_dense_destroy": ([vp], None),
         "vsb200_dense_export_halo": ([vp, vp, vp, C.POINTER(C.c_int32)], C.c_int),
-        "vsb200_dense_import_halo": ([vp, vp, vp, C.c_int32], C.c_int),
+        "vsb200_dense_import_halo": ([vp, vp, vp, C.POINTER(C.c_int32)], C.c_int),
     }
     missing = []
     for name, (argtypes, restype) in sigs.items():

@@ -59,6 +59,7 @@ struct vsb200_dense {
   // DenseSegmentation members (dense_segmentation.h:198-230)
   int input_frames = 0, chunk_id = 0, overlap_frames = 2, constraint_frames = 1;
   int max_region_id = 0, num_output_frames = 0, curr_chunk_start = 0;
+  bool import_pending = false;     // import_halo done, the group's first frame (slot 1) not pushed yet
   int buffered = 0;              // == feature_buffer_.size(): graph slots in use
   int max_slots = 0;
   int min_region_size = 0;
@@ -208,7 +209,7 @@ int vsb200_dense::add_frame_to_graph(int slot, const int* d_constraints) {
 int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int flow_stride, int64_t pts, int* n_ready, bool device_input) {
   if (n_ready) *n_ready = 0;
   if (!bgr || stride < w * 3) { set_error("push: bad frame buffer"); return VSB200_ERR_INVALID; }
-  if (use_flow && input_frames > 0 && !flow) { set_error("push: flow missing (created with use_flow)"); return VSB200_ERR_INVALID; }
+  if (use_flow && (input_frames > 0 || import_pending) && !flow) { set_error("push: flow missing (created with use_flow)"); return VSB200_ERR_INVALID; }
   if (buffered >= max_slots) { set_error("push: internal slot overflow"); return VSB200_ERR_INVALID; }
   ENG_CUDA(cudaSetDevice(o.device));
   pts_queue.push_back(pts);
@@ -226,7 +227,7 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
   }
   stats[7] += (o.presmoothing == 2) ? 3 : 1;
   if (use_flow) {
-    if (input_frames == 0 || !flow) {
+    if ((input_frames == 0 && !import_pending) || !flow) {
       h_flows[slot].clear();
       ENG_CUDA(cudaMemsetAsync(d_flows + (size_t)slot * n * 2, 0, (size_t)n * 2 * sizeof(float), stream));
     } else {
@@ -239,7 +240,14 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
       h2d_bytes += (double)n * 8;
     }
   }
-  ENG_RC(add_frame_to_graph(slot, nullptr));
+  if (import_pending) {
+    // first frame of a successor group: it is the predecessor's second overlap frame, re-added under the
+    // imported labels next to the virtual slot (ChunkBoundaryOutput, dense_segmentation.cpp:290-328)
+    ENG_RC(start_constrained_chunk());
+    import_pending = false;
+  } else {
+    ENG_RC(add_frame_to_graph(slot, nullptr));
+  }
   ENG_CUDA(cudaStreamSynchronize(stream));            // h_bgr is reused by the next push
   stats[0] += now_ms() - t0;
   ++buffered;
@@ -974,8 +982,8 @@ void vsb200_dense_stats(vsb200_dense* d, double out[9]) {
 
 void vsb200_dense_destroy(vsb200_dense* d) { delete d; }
 
-int vsb200_dense_export_halo(vsb200_dense* d, int32_t* dev_prev_out, int32_t* dev_last_out, int32_t* max_region_id) {
-  if (!d || !dev_prev_out || !dev_last_out || !max_region_id) return VSB200_ERR_INVALID;
+int vsb200_dense_export_halo(vsb200_dense* d, int32_t* dev_prev_out, int32_t* dev_last_out, int32_t chain_state[3]) {
+  if (!d || !dev_prev_out || !dev_last_out || !chain_state) return VSB200_ERR_INVALID;
   if (d->chunk_id == 0 || d->buffered != d->overlap_frames) {
     set_error("export_halo: only valid right after a chunk boundary");
     return VSB200_ERR_INVALID;
@@ -987,15 +995,34 @@ int vsb200_dense_export_halo(vsb200_dense* d, int32_t* dev_prev_out, int32_t* de
     set_error("export_halo: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return VSB200_ERR_CUDA;
   }
-  *max_region_id = d->max_region_id;
+  chain_state[0] = d->max_region_id;         // max_region_id_ (dense_segmentation.cpp:360-365)
+  chain_state[1] = d->chunk_id;              // id of the chunk the maps constrain
+  chain_state[2] = d->num_output_frames;     // frames output so far (hierarchy_frame_idx of the next chunk)
   return VSB200_OK;
 }
 
-int vsb200_dense_import_halo(vsb200_dense* d, const int32_t* dev_prev, const int32_t* dev_last, int32_t max_region_id) {
-  if (!d || !dev_prev || !dev_last) return VSB200_ERR_INVALID;
-  if (d->input_frames != 0) { set_error("import_halo must precede the first push"); return VSB200_ERR_INVALID; }
-  set_error("import_halo: pipelined seam (exact semantics) is not built yet; bench.py shards by independent groups");
-  return VSB200_ERR_UNSUPPORTED;
+// Successor side of the seam: puts a fresh engine into the state its predecessor is in right after
+// a chunk boundary -- constraint maps of the virtual slot and of slot 1, region-id counter, chunk
+// and frame counters.  The next push must be the frame of the second map (the predecessor's last
+// pushed frame); from there the chain continues exactly as one engine would have run it.
+int vsb200_dense_import_halo(vsb200_dense* d, const int32_t* dev_prev, const int32_t* dev_last, const int32_t chain_state[3]) {
+  if (!d || !dev_prev || !dev_last || !chain_state) return VSB200_ERR_INVALID;
+  if (d->input_frames != 0 || d->import_pending) { set_error("import_halo must precede the first push"); return VSB200_ERR_INVALID; }
+  if (chain_state[0] < 0 || chain_state[1] < 1 || chain_state[2] < 0) { set_error("import_halo: bad chain state"); return VSB200_ERR_INVALID; }
+  if (cudaSetDevice(d->o.device) != cudaSuccess ||
+      cudaMemcpyAsync(d->d_con_ids[0], dev_prev, (size_t)d->n * 4, cudaMemcpyDeviceToDevice, d->stream) != cudaSuccess ||
+      cudaMemcpyAsync(d->d_con_ids[1], dev_last, (size_t)d->n * 4, cudaMemcpyDeviceToDevice, d->stream) != cudaSuccess ||
+      cudaStreamSynchronize(d->stream) != cudaSuccess) {
+    set_error("import_halo: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return VSB200_ERR_CUDA;
+  }
+  d->max_region_id = chain_state[0];
+  d->chunk_id = chain_state[1];
+  d->num_output_frames = chain_state[2];
+  d->buffered = 1;                 // slot 0 = virtual copy of the predecessor's last output frame
+  d->curr_chunk_start = 1;
+  d->import_pending = true;
+  return VSB200_OK;
 }
 
 }  // extern "C"

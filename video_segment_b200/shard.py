@@ -53,3 +53,39 @@ def seam_exchange(halo_out: torch.Tensor, halo_in: torch.Tensor, max_region_id: 
     for r in reqs:
         r.wait()
     return (halo_in if rank > 0 else None), id_offsets([int(c.item()) for c in counts])
+
+
+def seam_vote(pred_map: torch.Tensor, succ_map: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Parallel seam (second strategy): the successor group segmented the shared frame
+    on its own; every region id it uses there is mapped to the predecessor id that covers most of its pixels.
+    pred_map / succ_map: int32 [H, W] id maps of the SAME frame (the predecessor's last overlap map and the
+    successor's first output frame), on any device.  Returns (succ_ids, pred_ids, overlap_px), succ_ids sorted
+    ascending; ties go to the smaller predecessor id.  Runs on the tensors' device (a handful of sort / unique
+    passes over H*W keys -- the exchange itself is the point, not this bookkeeping)."""
+    if pred_map.shape != succ_map.shape:
+        raise ValueError("seam_vote: the two maps must show the same frame")
+    s = succ_map.reshape(-1).to(torch.int64)
+    p = pred_map.reshape(-1).to(torch.int64)
+    ok = (s >= 0) & (p >= 0)
+    s, p = s[ok], p[ok]
+    if s.numel() == 0:
+        e = torch.empty(0, dtype=torch.int64, device=succ_map.device)
+        return e, e.clone(), e.clone()
+    pairs, counts = torch.unique((s << 32) | p, return_counts=True)          # sorted by (succ, pred)
+    ps, pp = pairs >> 32, pairs & 0xFFFFFFFF
+    # best predecessor per successor id: sort by (succ asc, count desc, pred asc) and keep the first of each run
+    order = torch.argsort(pp, stable=True)
+    order = order[torch.argsort(-counts[order], stable=True)]
+    order = order[torch.argsort(ps[order], stable=True)]
+    ps, pp, counts = ps[order], pp[order], counts[order]
+    first = torch.ones_like(ps, dtype=torch.bool)
+    first[1:] = ps[1:] != ps[:-1]
+    return ps[first], pp[first], counts[first]
+
+
+def relabel_table(succ_ids: torch.Tensor, pred_ids: torch.Tensor, num_succ_ids: int, id_offset: int) -> torch.Tensor:
+    """Successor-local region id -> id in the predecessor's numbering (regions visible in the shared frame)
+    or a fresh global id `id_offset + local id` (regions born later).  C2's exclusive prefix is id_offset."""
+    table = torch.arange(num_succ_ids, dtype=torch.int64, device=succ_ids.device) + int(id_offset)
+    table[succ_ids] = pred_ids
+    return table

@@ -87,6 +87,7 @@ class DenseSegmentationUnit:
         self.dense_seg_options = dense_seg_options or DenseSegmentationOptions()
         self.device = device
         self.want_id_maps = want_id_maps
+        self._imported = False
         self.want_proto = want_proto
         self._h = C.c_void_p()
         self.frame_width = self.frame_height = 0
@@ -156,7 +157,7 @@ class DenseSegmentationUnit:
             bgr = np.ascontiguousarray(bgr)
         stride = width_step if width_step is not None else bgr.strides[0]
         fl_ptr, fl_stride = None, 0
-        if self._use_flow and self.input_frames > 0:
+        if self._use_flow and (self.input_frames > 0 or self._imported):
             if flow is None:
                 raise ValueError("Flow always has to be passed or be absent.")      # dense_segmentation.cpp:139
             flow = np.ascontiguousarray(flow, np.float32)
@@ -176,12 +177,21 @@ class DenseSegmentationUnit:
         self.input_frames += 1
         return self._collect(n.value)
 
-    def export_halo(self, dev_prev_ptr: int, dev_last_ptr: int) -> int:
-        """Copies the two overlap frames' region-id maps into device buffers; returns max region id."""
-        m = C.c_int32()
-        check(lib().vsb200_dense_export_halo(self._h, C.c_void_p(dev_prev_ptr), C.c_void_p(dev_last_ptr), C.byref(m)),
+    def export_halo(self, dev_prev_ptr: int, dev_last_ptr: int) -> List[int]:
+        """Copies the two overlap frames' region-id maps into device buffers (int32 [h*w] each); returns the
+        chain state [max region id, id of the chunk the maps constrain, frames output so far]."""
+        st = (C.c_int32 * 3)()
+        check(lib().vsb200_dense_export_halo(self._h, C.c_void_p(dev_prev_ptr), C.c_void_p(dev_last_ptr), st),
               "vsb200_dense_export_halo")
-        return m.value
+        return [int(v) for v in st]
+
+    def import_halo(self, dev_prev_ptr: int, dev_last_ptr: int, chain_state) -> None:
+        """Successor side of the seam: must precede the first frame; the first frame pushed afterwards has to be
+        the predecessor's last pushed frame (the frame of the second id map)."""
+        st = (C.c_int32 * 3)(*[int(v) for v in chain_state])
+        check(lib().vsb200_dense_import_halo(self._h, C.c_void_p(dev_prev_ptr), C.c_void_p(dev_last_ptr), st),
+              "vsb200_dense_import_halo")
+        self._imported = True      # the group's first frame carries a flow field like any later frame
 
     def set_profiling(self, time_edge_kernel: bool = True) -> None:
         lib().vsb200_dense_set_profiling(self._h, int(time_edge_kernel))
