@@ -280,10 +280,22 @@ constexpr int kScUnc = 8;        // hub: may meet another un-finalised hub throu
 constexpr int kScCertYes = 32;     // cached verdict of subcluster_certified for this segment attempt
 constexpr int kScCertNo = 64;
 constexpr int kScUncAny = 16;    // hub: may meet a hub with the same constraint id through a shared sub-cluster (flags do not matter)
-constexpr unsigned long long kWindowTarget = 1ull << 18;   // live edges aimed at per window
+#ifndef VSB_WINDOW_TARGET
+#define VSB_WINDOW_TARGET (1ull << 18)
+#endif
+#ifndef VSB_RESIDUAL_SPLIT
+#define VSB_RESIDUAL_SPLIT 4096
+#endif
+#ifndef VSB_SEGMENT_MIN
+#define VSB_SEGMENT_MIN 2048
+#endif
+#ifndef VSB_GROUP_SCAN_MIN
+#define VSB_GROUP_SCAN_MIN 128
+#endif
+constexpr unsigned long long kWindowTarget = VSB_WINDOW_TARGET;   // live edges aimed at per window
 constexpr unsigned long long kWindowMin = 4096;            // smallest raw window
-constexpr unsigned long long kSegmentMin = 2048;           // segments are not halved below this many live edges
-constexpr unsigned long long kResidualSplit = 4096;        // uncertified edges that trigger a halving
+constexpr unsigned long long kSegmentMin = VSB_SEGMENT_MIN;           // segments are not halved below this many live edges
+constexpr unsigned long long kResidualSplit = VSB_RESIDUAL_SPLIT;        // uncertified edges that trigger a halving
 constexpr int kP1U = 8;                                     // edges per thread in flight in the prune pass
 
 // one atomic per converged group of lanes instead of one per live edge
@@ -409,7 +421,7 @@ constexpr unsigned long long kBlockRoundsLimit = 2048;   // residual lists up to
 // three grid barriers plus several dependent global loads, and a chain needs one round per link).
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanMax = 2048;
-constexpr unsigned long long kGroupScanMin = 1024;   // residuals above this are scanned group-parallel by all CTAs
+constexpr unsigned long long kGroupScanMin = VSB_GROUP_SCAN_MIN;   // residuals above this are scanned group-parallel by all CTAs
 constexpr int kScanHashBits = 13;                // 4 * kScanMax slots
 static_assert((1 << kScanHashBits) == 4 * kScanMax, "hash size");
 struct ScanShared;
