@@ -108,6 +108,19 @@ def test_synthetic_640x480_chunk(real_clip):
     _compare(got, ref, exact=False)
 
 
+def test_1080p_chunk_matches_oracle():
+    """BASELINE config C geometry against the oracle itself (one flushed 8-frame chunk, 133 M edges): every
+    frame must meet the IoU bar; the number of partition-exact frames is reported, not asserted."""
+    clip = synth_clip(3, 1920, 1080, 8)
+    got, batches, st = _run_gpu(clip)
+    ref = _run_oracle(clip)
+    ious = _compare(got, ref, exact=False)
+    same = sum(partition_equal(ob.id_map_from_result(r), g["id_map"]) for g, r in zip(got, ref))
+    print("1080p min IoU", min(ious), "partition-exact frames", same, "of", len(ref))
+    for g, r in zip(got, ref):
+        assert abs(len(g["region_id"]) - len(r["region_id"])) <= max(2, len(r["region_id"]) // 100)
+
+
 def test_flow_path_matches_oracle():
     pairs = list(synth_flow(21, 160, 120, 24))
     clip = [p[0] for p in pairs]
