@@ -161,6 +161,31 @@ size_t vsb200_sort_scratch_bytes(int num_lists, int width, int height);
 int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slots, int l1,
                          int min_region_size, int32_t* dev_labels_out, double* stats4, void* stream);
 
+/* ---- region stage, appearance descriptor (csrc/region_hist.cu) ---- */
+
+/* cv::cvtColor(CV_BGR2Lab) on 8-bit data, AppearanceExtractor (segmentation/region_descriptor.cpp:59-89, :73).
+ * dev_lab_out is dense [h][w][3].  Bit identical to OpenCV's integer path (cv2 4.13 over the whole cube). */
+int vsb200_bgr2lab(const uint8_t* dev_bgr, int row_stride_bytes, int width, int height, uint8_t* dev_lab_out,
+                   void* stream);
+/* Per-region Lab histograms, AppearanceDescriptor3D::AddFeatures (region_descriptor.cpp:97-111) ->
+ * ColorHistogram::AddPixelInterpolated / AddValueInterpolated (segmentation/histograms.cpp:140-211), for all
+ * regions of a frame at once: reset once per chunk set, add once per frame (BGR frame + its int32 region-id
+ * map, ids outside [0, n_regions) are skipped), finish = NormalizeToOne (histograms.cpp:340-360) into
+ * dev_hist_out [n_regions][lum_bins * color_bins * color_bins] (bin = l * color_bins^2 + a * color_bins + b)
+ * and the weight sums (pixel counts) into dev_weight_sum_out [n_regions] (may be NULL).
+ * RegionSegmentationOptions defaults: luminance_bins 10, color_bins 20 (region_segmentation.h:60-61). */
+size_t vsb200_region_hist_scratch_bytes(int n_regions, int lum_bins, int color_bins);
+int vsb200_region_hist_reset(void* dev_scratch, int n_regions, int lum_bins, int color_bins, void* stream);
+int vsb200_region_hist_add(const uint8_t* dev_bgr, int row_stride_bytes, const int32_t* dev_region_ids,
+                           int width, int height, int n_regions, int lum_bins, int color_bins,
+                           void* dev_scratch, void* stream);
+int vsb200_region_hist_finish(const void* dev_scratch, int n_regions, int lum_bins, int color_bins,
+                              float* dev_hist_out, float* dev_weight_sum_out, void* stream);
+/* AppearanceDescriptor3D::RegionDistance = ColorHistogram::ChiSquareDist (histograms.cpp:391-407) for region
+ * pairs dev_pairs [2 * n_pairs] (e.g. the neighbour pairs of the over-segmentation) -> dev_out [n_pairs]. */
+int vsb200_hist_chisquare(const float* dev_hist, int total_bins, const int32_t* dev_pairs, int n_pairs,
+                          float* dev_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,17 @@ void vso_dense_stage_seconds(vso_dense*, double out[5]);
 int vso_segment_chunk_labels(const float* frames, int w, int h, int t, int l1,
                              int min_region_size, int32_t* labels_out);
 
+/* ---- region stage, appearance descriptor (vso_region.cpp) ---- */
+/* cv::cvtColor(CV_BGR2Lab) on 8-bit data (region_descriptor.cpp:73); lab_out is dense [h][w][3]. */
+void vso_bgr2lab(const uint8_t* bgr, int w, int h, int row_stride, uint8_t* lab_out);
+/* AppearanceDescriptor3D::AddFeatures (region_descriptor.cpp:97-111) for every region of one frame. */
+void vso_region_hist_add(const uint8_t* lab, const int32_t* ids, int w, int h, int n_regions, int lum_bins,
+                         int color_bins, int exact, double* hist, double* weight_sum);
+/* ColorHistogram::NormalizeToOne (histograms.cpp:340-360). */
+void vso_hist_normalize(const double* hist, const double* weight_sum, int n_regions, int total_bins, int exact, float* out);
+/* ColorHistogram::ChiSquareDist (histograms.cpp:391-407) for region pairs [2 * n_pairs]. */
+void vso_hist_chisquare(const float* hist, int total_bins, const int32_t* pairs, int n_pairs, float* out);
+
 #ifdef __cplusplus
 }
 #endif

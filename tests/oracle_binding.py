@@ -110,6 +110,11 @@ def lib():
         L.vso_dense_last_chunk_merge_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.vso_dense_stage_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.vso_segment_chunk_labels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vso_bgr2lab.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vso_region_hist_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]
+        L.vso_hist_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vso_hist_chisquare.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -171,6 +176,42 @@ def temporal_weights(curr, prev, flow=None, l1=False) -> np.ndarray:
 
 def bucket_index(w: float) -> int:
     return lib().vso_bucket_index(float(w))
+
+
+def bgr2lab(bgr: np.ndarray) -> np.ndarray:
+    """cv::cvtColor(CV_BGR2Lab) on 8-bit data (region_descriptor.cpp:73)."""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w, 3), np.uint8)
+    lib().vso_bgr2lab(bgr.ctypes.data, w, h, w * 3, out.ctypes.data)
+    return out
+
+
+def region_hist(lab_frames, id_maps, n_regions: int, lum_bins: int = 10, color_bins: int = 20, exact: bool = False):
+    """AppearanceDescriptor3D over the frames of a chunk set: returns (normalised histograms float32
+    [n_regions, lum * col * col], weight sums float64 [n_regions]).  exact=False accumulates in float like the
+    reference, exact=True in double."""
+    total = lum_bins * color_bins * color_bins
+    hist = np.zeros((n_regions, total), np.float64)
+    wsum = np.zeros(n_regions, np.float64)
+    for lab, ids in zip(lab_frames, id_maps):
+        lab = np.ascontiguousarray(lab, np.uint8)
+        ids = np.ascontiguousarray(ids, np.int32)
+        h, w = ids.shape
+        lib().vso_region_hist_add(lab.ctypes.data, ids.ctypes.data, w, h, n_regions, lum_bins, color_bins, int(exact),
+                                  hist.ctypes.data, wsum.ctypes.data)
+    out = np.empty((n_regions, total), np.float32)
+    lib().vso_hist_normalize(hist.ctypes.data, wsum.ctypes.data, n_regions, total, int(exact), out.ctypes.data)
+    return out, wsum
+
+
+def hist_chisquare(hist: np.ndarray, pairs: np.ndarray) -> np.ndarray:
+    """ColorHistogram::ChiSquareDist (histograms.cpp:391-407) for region pairs [n, 2]."""
+    hist = np.ascontiguousarray(hist, np.float32)
+    pairs = np.ascontiguousarray(pairs, np.int32)
+    out = np.empty(len(pairs), np.float32)
+    lib().vso_hist_chisquare(hist.ctypes.data, hist.shape[1], pairs.ctypes.data, len(pairs), out.ctypes.data)
+    return out
 
 
 def segment_chunk_labels(frames_f32: np.ndarray, min_region_size: int, l1=False) -> np.ndarray:

@@ -183,3 +183,65 @@ def test_merge_min_region_size_property(K):
     lab = lab.cpu().numpy()
     _, counts = np.unique(lab, return_counts=True)
     assert (counts < minr).mean() < 0.02, (counts < minr).mean()
+
+
+# ---- region stage: appearance descriptor (csrc/region_hist.cu) ----
+
+def test_bgr2lab_bit_exact_over_the_colour_cube(K):
+    """Integer path: bit exact against the oracle (itself pinned to cv2 over the same cube, CPU suite)."""
+    r, g, b = np.meshgrid(np.arange(0, 256, 3), np.arange(256), np.arange(256), indexing="ij")     # 86 x 256 x 256 colours
+    cube = np.stack([b, g, r], -1).astype(np.uint8).reshape(-1, 256, 3)
+    got = K.bgr2lab(_dev(cube)).cpu().numpy()
+    assert np.array_equal(got, ob.bgr2lab(cube))
+    frame = synth_clip(12, 70, 45, 1)[0]                       # odd width: unaligned rows
+    assert np.array_equal(K.bgr2lab(_dev(frame)).cpu().numpy(), ob.bgr2lab(frame))
+
+
+@pytest.mark.parametrize("bins", [(10, 20), (4, 3)])
+def test_region_hist_parity(K, bins):
+    """Floating point: the kernel sums 2^-26 fixed-point weights (order independent), the reference sums floats in
+    raster order.  Tolerances: 1e-7 against the oracle's exact (double) accumulation, 2e-5 against its float
+    accumulation (the reference's own rounding noise), on L1-normalised bins in [0, 1]."""
+    import torch
+    lum, col = bins
+    clip = synth_clip(13, 160, 120, 3)
+    rng = np.random.default_rng(8)
+    nr = 23
+    blocks = rng.integers(-1, nr + 1, size=(3, 8, 10)).astype(np.int32)       # coarse region maps; -1 / nr = no region
+    ids = [np.kron(bm, np.ones((15, 16), np.int32)) for bm in blocks]
+    labs = [ob.bgr2lab(f) for f in clip]
+    exact, wsum = ob.region_hist(labs, ids, nr, lum, col, exact=True)
+    like_ref, _ = ob.region_hist(labs, ids, nr, lum, col, exact=False)
+    hist, w = K.region_hist([_dev(f) for f in clip], [_dev(m) for m in ids], nr, lum, col)
+    hist, w = hist.cpu().numpy(), w.cpu().numpy()
+    assert np.array_equal(w, wsum.astype(np.float32))
+    assert np.abs(hist - exact).max() <= 1e-7
+    assert np.abs(hist - like_ref).max() <= 2e-5
+    assert np.array_equal(hist > 0, exact > 0) or np.abs(hist - exact)[(hist > 0) != (exact > 0)].max() <= 2e-8
+    # empty region: all-zero histogram, zero weight
+    hist2, w2 = K.region_hist([_dev(clip[0])], [_dev(np.zeros((120, 160), np.int32))], 2, lum, col)
+    assert float(w2[1]) == 0 and float(hist2[1].abs().sum()) == 0 and abs(float(hist2[0].sum()) - 1) <= 1e-5
+    # chi-square distances between neighbouring regions
+    pairs = np.int32([[0, 1], [1, 0], [2, 2], [3, 22], [5, 9]])
+    d = K.hist_chisquare(_dev(hist), _dev(pairs)).cpu().numpy()
+    assert np.abs(d - ob.hist_chisquare(hist, pairs)).max() <= 1e-6
+    assert d[2] == 0 and abs(d[0] - d[1]) <= 1e-7
+
+
+def test_region_hist_on_the_engine_output(K):
+    """End of the dense stage -> start of the region stage: id maps from the streaming engine feed the descriptor."""
+    from video_segment_b200.unit import DenseSegmentationUnit
+    clip = synth_clip(14, 160, 120, 6)
+    u = DenseSegmentationUnit(want_id_maps=True)
+    assert u.open_streams(160, 120)
+    out = []
+    for f in clip:
+        out += u.process_frame(f)
+    out += u.post_process()
+    u.close()
+    nr = 1 + max(int(o["id_map"].max()) for o in out)
+    ids = [o["id_map"].astype(np.int32) for o in out]
+    hist, w = K.region_hist([_dev(f) for f in clip], [_dev(m) for m in ids], nr)
+    exact, wsum = ob.region_hist([ob.bgr2lab(f) for f in clip], ids, nr, exact=True)
+    assert np.array_equal(w.cpu().numpy(), wsum.astype(np.float32)) and int(wsum.sum()) == 6 * 160 * 120
+    assert np.abs(hist.cpu().numpy() - exact).max() <= 1e-7

@@ -144,3 +144,84 @@ def test_threaded_oracle_equals_serial(real_clip):
             res += o.push(f)
         outs.append(np.stack([ob.id_map_from_result(r) for r in res]))
     assert np.array_equal(outs[0], outs[1])
+
+
+# ---- region stage: appearance descriptor (oracle/vso_region.cpp) ----
+
+def _lab_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lab_bgr2lab_cv2.npz"))
+
+
+def test_bgr2lab_matches_cv2_golden_vectors_and_full_cube_checksum():
+    """Third-party arithmetic (cv::cvtColor(CV_BGR2Lab), region_descriptor.cpp:73): pinned by cv2 4.13 answers."""
+    import hashlib
+    g = _lab_golden()
+    got = ob.bgr2lab(g["sample_bgr"].reshape(-1, 1, 3)).reshape(-1, 3)
+    assert np.array_equal(got, g["sample_lab"])
+    r, gg, b = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")
+    cube = np.stack([b, gg, r], -1).astype(np.uint8).reshape(65536, 256, 3)
+    digest = hashlib.sha256(ob.bgr2lab(cube).tobytes()).digest()
+    assert digest == g["cube_sha256"].tobytes()
+    # known answers: black, white, primaries (OpenCV 8-bit Lab: L * 255 / 100, a + 128, b + 128)
+    px = np.uint8([[[0, 0, 0]], [[255, 255, 255]], [[0, 0, 255]], [[0, 255, 0]], [[255, 0, 0]]])
+    assert ob.bgr2lab(px).reshape(-1, 3).tolist() == [[0, 128, 128], [255, 128, 128], [136, 208, 195], [224, 42, 211], [82, 207, 20]]
+
+
+def _numpy_region_hist(lab, ids, n_regions, lum_bins, color_bins):
+    """Independent float64 restatement of AddValueInterpolated (histograms.cpp:140-204) with numpy scatter-adds."""
+    total = lum_bins * color_bins * color_bins
+    hist = np.zeros((n_regions, total))
+    ids = ids.reshape(-1)
+    px = lab.reshape(-1, 3)
+    ok = (ids >= 0) & (ids < n_regions)
+    f = np.float32
+    xb = px[:, 0].astype(f) * f(1.0 / 255.0) * f(lum_bins - 1)
+    yb = px[:, 1].astype(f) * f(1.0 / 255.0) * f(color_bins - 1)
+    zb = px[:, 2].astype(f) * f(1.0 / 255.0) * f(color_bins - 1)
+    ix, iy, iz = xb.astype(np.int32), yb.astype(np.int32), zb.astype(np.int32)
+    dx, dy, dz = xb - ix.astype(f), yb - iy.astype(f), zb - iz.astype(f)
+    for a in range(2):
+        for b in range(2):
+            for c in range(2):
+                bx = ix + (a & (dx >= f(1e-6))); by = iy + (b & (dy >= f(1e-6))); bz = iz + (c & (dz >= f(1e-6)))
+                wv = ((dx if a else f(1) - dx) * (dy if b else f(1) - dy)) * (dz if c else f(1) - dz)
+                np.add.at(hist, (ids[ok], (bx * color_bins * color_bins + by * color_bins + bz)[ok]), wv[ok].astype(np.float64))
+    cnt = np.bincount(ids[ok], minlength=n_regions).astype(np.float64)
+    return hist, cnt
+
+
+def test_region_hist_against_independent_restatement():
+    rng = np.random.default_rng(5)
+    h, w, nr = 40, 56, 7
+    lab = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    lab[:4] = 255                                   # top of the range: last bin, zero fraction
+    lab[4:8, :, 1] = 0
+    ids = rng.integers(-1, nr + 1, size=(h, w)).astype(np.int32)   # -1 and nr: pixels outside every region
+    for lum, col in ((10, 20), (4, 3)):
+        ref, cnt = _numpy_region_hist(lab, ids, nr, lum, col)
+        exact, wsum = ob.region_hist([lab], [ids], nr, lum, col, exact=True)
+        assert np.array_equal(wsum, cnt)
+        assert np.abs(exact - ref / np.maximum(cnt, 1)[:, None]).max() <= 1e-7
+        like_ref, _ = ob.region_hist([lab], [ids], nr, lum, col, exact=False)
+        assert np.abs(like_ref - exact).max() <= 1e-5      # float accumulation noise of the reference itself
+        assert np.abs(like_ref.sum(1) - (cnt > 0)).max() <= 1e-4      # L1 norm 1 (NormalizeToOne)
+    # two frames accumulate into the same descriptor (3-D regions)
+    two, w2 = ob.region_hist([lab, lab[::-1]], [ids, ids[::-1]], nr, exact=True)
+    one, w1 = ob.region_hist([lab], [ids], nr, exact=True)
+    assert np.array_equal(w2, 2 * w1) and np.abs(two - one).max() <= 1e-7
+
+
+def test_hist_chisquare_properties():
+    rng = np.random.default_rng(6)
+    hist = rng.random((5, 4000)).astype(np.float32)
+    hist[:, rng.random(4000) < 0.7] = 0            # sparse like real descriptors
+    hist /= hist.sum(1, keepdims=True)
+    hist[4] = 0                                     # an empty region
+    pairs = np.int32([[0, 1], [1, 0], [2, 2], [3, 4], [0, 3]])
+    d = ob.hist_chisquare(hist, pairs)
+    a, b = hist[pairs[:, 0]].astype(np.float64), hist[pairs[:, 1]].astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = 0.5 * np.where(a + b > 1e-12, (a - b) ** 2 / (a + b), 0).sum(1)
+    assert np.abs(d - ref).max() <= 1e-6
+    assert d[0] == d[1] and d[2] == 0 and abs(d[3] - 0.5) <= 1e-6 and np.all(d <= 1.0 + 1e-6)

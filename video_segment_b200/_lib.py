@@ -47,6 +47,8 @@ EXPORTED_SYMBOLS = [
     "vsb200_dense_destroy", "vsb200_dense_export_halo", "vsb200_dense_import_halo",
     "vsb200_preprocess_scratch_bytes", "vsb200_preprocess", "vsb200_edge_build",
     "vsb200_bucket_index", "vsb200_sort_edges", "vsb200_sort_scratch_bytes", "vsb200_segment_chunk",
+    "vsb200_bgr2lab", "vsb200_region_hist_scratch_bytes", "vsb200_region_hist_reset", "vsb200_region_hist_add",
+    "vsb200_region_hist_finish", "vsb200_hist_chisquare",
 ]
 
 _lib = None
@@ -87,6 +89,12 @@ def lib() -> C.CDLL:
         "vsb200_dense_destroy": ([vp], None),
         "vsb200_dense_export_halo": ([vp, vp, vp, C.POINTER(C.c_int32)], C.c_int),
         "vsb200_dense_import_halo": ([vp, vp, vp, C.POINTER(C.c_int32)], C.c_int),
+        "vsb200_bgr2lab": ([vp, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
+        "vsb200_region_hist_scratch_bytes": ([C.c_int, C.c_int, C.c_int], C.c_size_t),
+        "vsb200_region_hist_reset": ([vp, C.c_int, C.c_int, C.c_int, vp], C.c_int),
+        "vsb200_region_hist_add": ([vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
+        "vsb200_region_hist_finish": ([vp, C.c_int, C.c_int, C.c_int, vp, vp, vp], C.c_int),
+        "vsb200_hist_chisquare": ([vp, C.c_int, vp, C.c_int, vp, vp], C.c_int),
     }
     missing = []
     for name, (argtypes, restype) in sigs.items():

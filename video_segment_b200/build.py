@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvsb200.so")
-SOURCES = ["preprocess.cu", "edges.cu", "sort.cu", "merge.cu", "results.cu", "capi_kernels.cu", "engine.cu"]
+SOURCES = ["preprocess.cu", "edges.cu", "sort.cu", "merge.cu", "results.cu", "region_hist.cu", "capi_kernels.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp", ".inc"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vsb200.h"))
     objs = []
     procs = []

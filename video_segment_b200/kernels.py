@@ -77,3 +77,46 @@ def segment_chunk(frames: torch.Tensor, min_region_size: int, l1: bool = False):
     check(lib().vsb200_segment_chunk(_ptr(frames), w, h, t, int(l1), int(min_region_size), _ptr(labels), stats,
                                      _stream()), "vsb200_segment_chunk")
     return labels, list(stats)
+
+
+def bgr2lab(bgr: torch.Tensor) -> torch.Tensor:
+    """cv::cvtColor(CV_BGR2Lab) on 8-bit data (region_descriptor.cpp:73): (H, W, 3) uint8 -> (H, W, 3) uint8."""
+    assert bgr.is_cuda and bgr.dtype == torch.uint8 and bgr.is_contiguous()
+    h, w, _ = bgr.shape
+    out = torch.empty_like(bgr)
+    check(lib().vsb200_bgr2lab(_ptr(bgr), w * 3, w, h, _ptr(out), _stream()), "vsb200_bgr2lab")
+    return out
+
+
+def region_hist(bgr_frames, id_maps, n_regions: int, lum_bins: int = 10, color_bins: int = 20):
+    """AppearanceDescriptor3D of every region over the frames of a chunk set (region_descriptor.cpp:97-111,
+    histograms.cpp:140-211,340-360).  bgr_frames: (H, W, 3) uint8 tensors, id_maps: (H, W) int32 region ids.
+    Returns (normalised histograms float32 [n_regions, lum * col * col], weight sums float32 [n_regions])."""
+    dev = bgr_frames[0].device
+    total = lum_bins * color_bins * color_bins
+    sb = lib().vsb200_region_hist_scratch_bytes(n_regions, lum_bins, color_bins)
+    if sb == 0:
+        raise ValueError("region_hist: bad histogram geometry")
+    scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+    check(lib().vsb200_region_hist_reset(_ptr(scratch), n_regions, lum_bins, color_bins, _stream()), "vsb200_region_hist_reset")
+    for bgr, ids in zip(bgr_frames, id_maps):
+        assert bgr.is_cuda and bgr.dtype == torch.uint8 and bgr.is_contiguous()
+        assert ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous()
+        h, w, _ = bgr.shape
+        check(lib().vsb200_region_hist_add(_ptr(bgr), w * 3, _ptr(ids), w, h, n_regions, lum_bins, color_bins, _ptr(scratch),
+                                           _stream()), "vsb200_region_hist_add")
+    hist = torch.empty((n_regions, total), dtype=torch.float32, device=dev)
+    wsum = torch.empty(n_regions, dtype=torch.float32, device=dev)
+    check(lib().vsb200_region_hist_finish(_ptr(scratch), n_regions, lum_bins, color_bins, _ptr(hist), _ptr(wsum), _stream()),
+          "vsb200_region_hist_finish")
+    return hist, wsum
+
+
+def hist_chisquare(hist: torch.Tensor, pairs: torch.Tensor) -> torch.Tensor:
+    """ColorHistogram::ChiSquareDist (histograms.cpp:391-407) for region pairs (n, 2) int32."""
+    assert hist.is_cuda and hist.dtype == torch.float32 and hist.is_contiguous()
+    assert pairs.is_cuda and pairs.dtype == torch.int32 and pairs.is_contiguous()
+    out = torch.empty(pairs.shape[0], dtype=torch.float32, device=hist.device)
+    check(lib().vsb200_hist_chisquare(_ptr(hist), hist.shape[1], _ptr(pairs), pairs.shape[0], _ptr(out), _stream()),
+          "vsb200_hist_chisquare")
+    return out
