@@ -89,7 +89,7 @@ void vso_hist_normalize(const double* hist, const double* weight_sum, int n_regi
     if (exact) {
       for (int b = 0; b < total_bins; ++b) O[b] = (float)(H[b] / weight_sum[r]);
     } else {
-      const float denom = 1.0f / (float)weight_sum[r];
+      const float denom = 1.0f / weight_sum[r];      // as written in the reference: double division, rounded to float
       for (int b = 0; b < total_bins; ++b) O[b] = (float)H[b] * denom;
     }
   }

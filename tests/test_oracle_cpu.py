@@ -225,3 +225,53 @@ def test_hist_chisquare_properties():
         ref = 0.5 * np.where(a + b > 1e-12, (a - b) ** 2 / (a + b), 0).sum(1)
     assert np.abs(d - ref).max() <= 1e-6
     assert d[0] == d[1] and d[2] == 0 and abs(d[3] - 0.5) <= 1e-6 and np.all(d <= 1.0 + 1e-6)
+
+
+# ---- the reference's own ColorHistogram (oracle/_ref, compiled unmodified from /root/reference) ----
+
+def _ref_hist_lib():
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "libref_hist.so")
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_hist.so not built (needs /root/reference)")
+    L = C.CDLL(path)
+    L.ref_color_hist.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.ref_color_hist.restype = C.c_double
+    L.ref_color_hist_chisquare.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ref_color_hist_chisquare.restype = C.c_float
+    return L
+
+
+@pytest.mark.parametrize("bins", [(10, 20), (4, 3), (16, 16)])
+def test_region_hist_oracle_equals_reference_color_histogram(bins):
+    """Pins oracle/vso_region.cpp to the reference itself: histograms.cpp compiled as it lies (glog stand-in only)."""
+    L = _ref_hist_lib()
+    lum, col = bins
+    total = lum * col * col
+    rng = np.random.default_rng(17)
+    frame = synth_clip(15, 96, 64, 1)[0]
+    lab = ob.bgr2lab(frame)
+    lab[:2] = 255
+    lab[2:4] = 0
+    ids = np.kron(rng.integers(0, 5, size=(8, 8)).astype(np.int32), np.ones((8, 12), np.int32))
+    mine, wsum = ob.region_hist([lab], [ids], 5, lum, col, exact=False)
+    sets = []
+    for r in range(5):
+        px = np.ascontiguousarray(lab[ids == r])                    # raster order == scan-interval order
+        sets.append(px)
+        out = np.zeros(total, np.float32)
+        w = L.ref_color_hist(px.ctypes.data, len(px), lum, col, out.ctypes.data)
+        assert w == wsum[r] == len(px)
+        assert np.array_equal(out, mine[r]), (r, np.abs(out - mine[r]).max())
+    pairs = np.int32([[0, 1], [1, 2], [3, 3], [4, 0]])
+    d = ob.hist_chisquare(mine, pairs)
+    for (a, b), dv in zip(pairs, d):
+        ref_dense = L.ref_color_hist_chisquare(sets[a].ctypes.data, len(sets[a]), sets[b].ctypes.data, len(sets[b]), lum, col, 0)
+        ref_sparse = L.ref_color_hist_chisquare(sets[a].ctypes.data, len(sets[a]), sets[b].ctypes.data, len(sets[b]), lum, col, 1)
+        assert dv == ref_dense
+        assert abs(dv - ref_sparse) <= 1e-7          # the hash map walks the bins in another order (double sum)
