@@ -3,12 +3,16 @@
  * The oracle is a dependency-free C++17 restatement of the reference's dense
  * over-segmentation path (videosegmentation/video_segment @ c930c455).  Every
  * function cites the reference file:line it follows (paths relative to the
- * reference root).  PARITY UNPINNED: the reference ships no tests, golden
- * vectors or fixtures for this path and cannot be built
- * in this image (needs OpenCV 2.4 / FFmpeg 2.2 / glog / gflags / boost /
- * protobuf), so this restatement is itself the pin.  Third-party arithmetic
- * (cv::Mat::convertTo, cv::copyMakeBorder, cv::minMaxLoc) is cross-checked
- * against Python cv2 by tests/golden/make_golden.py.
+ * reference root).  PINNING: the reference ships no tests, golden vectors or
+ * fixtures for this path and cannot be built in this
+ * image (needs OpenCV 2.4 / FFmpeg 2.2 / gflags / boost / protobuf), but its
+ * pixel distances, FastSegmentationGraph (the merge) and ColorHistogram compile
+ * unmodified into oracle/_ref (Makefile target _ref, stand-ins in ref_shim/)
+ * and tests/test_oracle_cpu.py holds this restatement bit-identical /
+ * partition-identical to them.  Third-party arithmetic (cv::Mat::convertTo,
+ * cv::copyMakeBorder, cv::minMaxLoc, 8-bit cv::cvtColor BGR2Lab) is pinned by
+ * cv2 golden vectors (tests/golden/).  PARITY UNPINNED for the rest: bilateral
+ * filter and result shaping (N4, RLE, tubes, ids, shape moments, proto).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product

@@ -15,12 +15,16 @@
 
 namespace vso {
 
-// pixel_distance.h:141-148
+// pixel_distance.h:141-148.  The reference writes unqualified fabs() after including only <cmath>: with GCC /
+// libstdc++ that is ::fabs(double), so the three absolute differences are summed and scaled in DOUBLE and rounded to
+// float once on return (found by compiling the reference's own header into oracle/_ref; float arithmetic differs in
+// the last bit for about one weight in five).  ColorDiff3L2's unqualified sqrt() is ::sqrt(double) in the same way,
+// which rounds like sqrtf.
 float ColorDiff3L1(const float* p1, const float* p2) {
   const float diff_1 = p1[0] - p2[0];
   const float diff_2 = p1[1] - p2[1];
   const float diff_3 = p1[2] - p2[2];
-  return (std::fabs(diff_1) + std::fabs(diff_2) + std::fabs(diff_3)) * (1.0f / 3.0f);
+  return (float)((std::fabs((double)diff_1) + std::fabs((double)diff_2) + std::fabs((double)diff_3)) * (double)(1.0f / 3.0f));
 }
 
 // pixel_distance.h:150-157

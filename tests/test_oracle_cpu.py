@@ -275,3 +275,69 @@ def test_region_hist_oracle_equals_reference_color_histogram(bins):
         ref_sparse = L.ref_color_hist_chisquare(sets[a].ctypes.data, len(sets[a]), sets[b].ctypes.data, len(sets[b]), lum, col, 1)
         assert dv == ref_dense
         assert abs(dv - ref_sparse) <= 1e-7          # the hash map walks the bins in another order (double sum)
+
+
+# ---- the reference's own FastSegmentationGraph + pixel distances (oracle/_ref/libref_graph.so) ----
+
+def _ref_graph_lib():
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "libref_graph.so")
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_graph.so not built (needs /root/reference)")
+    L = C.CDLL(path)
+    L.ref_segment_chunk_labels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_bucket_index.argtypes = [C.c_float]
+    return L
+
+
+def _ref_segment(L, frames, min_region_size, l1=False, force_constraints=True):
+    t, h, w, _ = frames.shape
+    frames = np.ascontiguousarray(frames, np.float32)
+    labels = np.empty((t, h, w), np.int32)
+    sp = np.empty((t, h, w, 4), np.float32)
+    tp = np.empty((t, h, w, 9), np.float32)
+    L.ref_segment_chunk_labels(frames.ctypes.data, w, h, t, int(l1), int(min_region_size), int(force_constraints),
+                               labels.ctypes.data, sp.ctypes.data, tp.ctypes.data)
+    return labels, sp, tp
+
+
+def _same_partition(a, b):
+    a, b = a.reshape(-1), b.reshape(-1)
+    _, ia = np.unique(a, return_inverse=True)
+    _, ib = np.unique(b, return_inverse=True)
+    pairs = np.unique(np.stack([ia, ib], 1), axis=0)
+    return len(pairs) == ia.max() + 1 == ib.max() + 1
+
+
+@pytest.mark.parametrize("case", ["real", "synth", "synth_l1", "tiny_regions"])
+def test_merge_oracle_equals_reference_segmentation_graph(case, real_clip):
+    """Pins the oracle's merge (vso_graph.cpp) and edge weights to the reference's own code: FastSegmentationGraph::
+    SegmentGraph / MergeRegions / ColorMeanDescriptorTraits and the CvMat distance walkers, compiled as they lie."""
+    L = _ref_graph_lib()
+    l1 = case == "synth_l1"
+    if case == "real":
+        clip = real_clip[:10]
+    elif case == "tiny_regions":
+        clip = synth_clip(23, 40, 32, 5)
+    else:
+        clip = synth_clip(22, 96, 72, 6)
+    frames = np.stack([ob.preprocess(f) for f in clip])
+    t, h, w, _ = frames.shape
+    mins = 4 if case == "tiny_regions" else int(0.01 * w * 0.01 * h * t) or 1    # dense_segmentation.cpp: frac^2 * w * h * frames
+    ref_labels, sp, tp = _ref_segment(L, frames, mins, l1)
+    # edge weights: bit identical to the reference's walkers
+    for k in range(t):
+        assert np.array_equal(ob.spatial_weights(frames[k], l1), sp[k].transpose(2, 0, 1))
+        if k:
+            assert np.array_equal(ob.temporal_weights(frames[k], frames[k - 1], None, l1), tp[k].transpose(2, 0, 1))
+    for wv in np.concatenate([sp.reshape(-1)[::97], np.float32([0, 1, 0.5, 1e10])]):
+        if wv >= 0:
+            assert ob.bucket_index(float(wv)) == L.ref_bucket_index(float(wv))
+    # the merge: identical partition of the voxels
+    mine = ob.segment_chunk_labels(frames, mins, l1)
+    assert _same_partition(mine, ref_labels)
+    assert len(np.unique(ref_labels)) > 1

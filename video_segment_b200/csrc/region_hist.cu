@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) hist_chisquare_kernel(const float* __rest
   for (int b = (int)lane; b < total; b += 32) {
     const float a = __ldg(&A[b]), c = __ldg(&B[b]);
     const float add = a + c;
-    if (fabsf(add) > 1e-12f) {
+    if (fabs((double)add) > 1e-12) {              // double comparison, as written in the reference
       const float sub = a - c;
       sum += (double)(sub * sub / add);
     }
