@@ -1,0 +1,26 @@
+// TEST INFRASTRUCTURE ONLY.  Stand-in for <opencv2/imgproc/imgproc.hpp>: cv::copyMakeBorder with BORDER_REPLICATE,
+// the one imgproc call of the reference's imagefilter/image_filter.cpp (:206-207).  Semantics checked against cv2 4.13
+// golden vectors (tests/golden/cv2_thirdparty.npz): every border texel copies the nearest source texel.
+#ifndef VSO_REF_SHIM_OPENCV_IMGPROC_HPP_
+#define VSO_REF_SHIM_OPENCV_IMGPROC_HPP_
+#include <cstring>
+#include "opencv2/core/core.hpp"
+namespace cv {
+enum { BORDER_REPLICATE = 1 };
+inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int border_type) {
+  (void)border_type;
+  (void)bottom;
+  (void)right;
+  const size_t es = src.elemSize();
+  for (int y = 0; y < dst.rows; ++y) {
+    int sy = y - top;
+    sy = sy < 0 ? 0 : (sy >= src.rows ? src.rows - 1 : sy);
+    for (int x = 0; x < dst.cols; ++x) {
+      int sx = x - left;
+      sx = sx < 0 ? 0 : (sx >= src.cols ? src.cols - 1 : sx);
+      std::memcpy(dst.ptr<uchar>(y) + (size_t)x * es, src.ptr<uchar>(sy) + (size_t)sx * es, es);
+    }
+  }
+}
+}  // namespace cv
+#endif

@@ -341,3 +341,54 @@ def test_merge_oracle_equals_reference_segmentation_graph(case, real_clip):
     mine = ob.segment_chunk_labels(frames, mins, l1)
     assert _same_partition(mine, ref_labels)
     assert len(np.unique(ref_labels)) > 1
+
+
+# ---- the reference's own BilateralFilter (oracle/_ref/libref_filter.so) ----
+
+def _ref_filter_lib():
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "libref_filter.so")
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_filter.so not built (needs /root/reference)")
+    L = C.CDLL(path)
+    L.ref_preprocess_bilateral.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    L.ref_bilateral_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("case", ["real", "synth", "flat", "two_level", "tiny", "odd"])
+def test_preprocess_oracle_equals_reference_bilateral_filter(case, real_clip):
+    """Pins the oracle's PreprocessFeatures (vso_preprocess.cpp: convert, replicate border, exp LUT, 49-tap bilateral
+    filter) bit for bit to the reference's own imagefilter::BilateralFilter compiled as it lies (image_filter.cpp:184-277)."""
+    L = _ref_filter_lib()
+    rng = np.random.default_rng(5)
+    if case == "real":
+        frames = [real_clip[0], real_clip[13]]
+    elif case == "synth":
+        frames = list(synth_clip(31, 96, 72, 2))
+    elif case == "flat":              # max == min: the 1e-3 floor of diff_range, every LUT index 0
+        frames = [np.full((20, 24, 3), 77, np.uint8)]
+    elif case == "two_level":         # narrow value range: scale is large, LUT reaches its zero tail
+        frames = [(rng.integers(0, 2, (33, 47, 3)) * 3 + 100).astype(np.uint8)]
+    elif case == "tiny":              # about the filter radius: the window is mostly replicated border.  (The reference
+        # itself never returns for height < 8: its ParallelFor grain is height / 8 = 0, image_filter.cpp:255.)
+        frames = [rng.integers(0, 256, (8, 5, 3), dtype=np.uint8), rng.integers(0, 256, (9, 1, 3), dtype=np.uint8)]
+    else:
+        frames = [rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)]
+    for f in frames:
+        f = np.ascontiguousarray(f)
+        h, w, _ = f.shape
+        ref = np.empty((h, w, 3), np.float32)
+        L.ref_preprocess_bilateral(f.ctypes.data, w, h, 3 * w, 3.0, 0.25, ref.ctypes.data)
+        mine = ob.preprocess(f)
+        assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+        # the filter alone, other sigmas (radius 2 and 6)
+        img = ob.convert_u8(f)
+        for ss, sc in ((1.5, 0.1), (4.0, 0.5)):
+            ref2 = np.empty_like(img)
+            L.ref_bilateral_f32(img.ctypes.data, w, h, 3, ss, sc, ref2.ctypes.data)
+            assert np.array_equal(ob.bilateral(img, ss, sc).view(np.uint32), ref2.view(np.uint32))
