@@ -5,6 +5,7 @@
 #define VSO_REF_SHIM_OPENCV_IMGPROC_HPP_
 #include <cstring>
 #include "opencv2/core/core.hpp"
+enum { CV_BGR2Lab = 44 };
 namespace cv {
 enum { BORDER_REPLICATE = 1 };
 inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int border_type) {
@@ -22,5 +23,12 @@ inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int le
     }
   }
 }
+// Region-stage feature extraction (region_descriptor.cpp:59-89) is linked for its vtables only in oracle/_ref; the
+// descriptor oracle is pinned through histograms.cpp and cv2 golden vectors instead.  Abort if reached.
+inline void cvtColor(const Mat&, Mat&, int, int = 0) { std::abort(); }
+inline Scalar mean(const Mat&) { std::abort(); }
+// Not on the default path (PRESMOOTH_GAUSSIAN, compute_vectorization): third-party algorithms, abort if reached.
+inline void GaussianBlur(const Mat&, Mat&, Size, double, double = 0, int = 4) { std::abort(); }
+template <class A, class B> inline void approxPolyDP(const A&, B&, double, bool) { std::abort(); }
 }  // namespace cv
 #endif

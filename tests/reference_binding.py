@@ -1,0 +1,90 @@
+"""ctypes binding of oracle/_ref/libref_results.so: the REFERENCE's own streaming over-segmentation
+(DenseSegmentation / Segmentation / DenseSegmentationGraph / FastSegmentationGraph / BilateralFilter ...) compiled
+unmodified from /root/reference by `make -C oracle _ref` (oracle/ref_results_wrap.cpp, stand-ins in oracle/ref_shim/).
+TEST INFRASTRUCTURE ONLY: used by tests/ to pin the oracle and by bench.py's CPU legs (cpu_baseline kind "reference");
+never by the product package.  The library is built where /root/reference exists and travels to the GPU box as a
+prebuilt file; nothing here reads /root/reference at run time."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle_binding import FrameResult, default_opts, result_to_dict
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_ROOT, "oracle", "_ref", "libref_results.so")
+_lib = None
+
+
+def available(build: bool = True) -> bool:
+    """True if the compiled reference is there (built on demand where the reference sources are mounted)."""
+    if build and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.ref_dense_create.restype = C.c_void_p
+        L.ref_dense_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int]
+        L.ref_dense_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_dense_flush.argtypes = [C.c_void_p]
+        L.ref_dense_pop.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_dense_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class ReferenceDense:
+    """The reference's DenseSegmentation behind the call shape of oracle_binding.OracleDense."""
+
+    def __init__(self, width, height, use_flow=False, **opts):
+        self.w, self.h, self.use_flow = width, height, use_flow
+        o = default_opts(**opts)
+        if o.presmoothing == 1:
+            raise ValueError("PRESMOOTH_GAUSSIAN needs cv::GaussianBlur (third party, not compiled in)")
+        if o.chunk_size < 3 or min(int(o.chunk_overlap_ratio * o.chunk_size + 0.5), 2) < 2:
+            # dense_segmentation.cpp:58-62 takes min(overlap, 2): with fewer than 2 overlap frames the reference reads
+            # overlap_segmentations_[1] out of bounds at the first chunk boundary (:304-306) and crashes.
+            raise ValueError("the reference needs at least 2 overlap frames (chunk_overlap_ratio * chunk_size >= 1.5)")
+        self._h = lib().ref_dense_create(o.presmoothing, o.frac_min_region_size, o.chunk_size, o.chunk_overlap_ratio,
+                                         o.num_constraint_frames, o.enforce_n4_connectivity,
+                                         o.enforce_spatial_connectedness, o.color_distance, width, height, int(use_flow))
+        self._n = 0
+
+    def push(self, bgr, flow=None, pts=None):
+        bgr = np.ascontiguousarray(bgr)
+        fl = None
+        if self.use_flow and self._n > 0:
+            fl = np.ascontiguousarray(flow, np.float32)
+        n = lib().ref_dense_push(self._h, bgr.ctypes.data, self.w * 3, None if fl is None else fl.ctypes.data, self.w * 8)
+        self._n += 1
+        return self._pop(n)
+
+    def flush(self):
+        return self._pop(lib().ref_dense_flush(self._h))
+
+    def _pop(self, n):
+        out = []
+        for _ in range(n):
+            r = FrameResult()
+            assert lib().ref_dense_pop(self._h, C.byref(r)) == 0
+            out.append(result_to_dict(r))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().ref_dense_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -392,3 +392,37 @@ def test_preprocess_oracle_equals_reference_bilateral_filter(case, real_clip):
             ref2 = np.empty_like(img)
             L.ref_bilateral_f32(img.ctypes.data, w, h, 3, ss, sc, ref2.ctypes.data)
             assert np.array_equal(ob.bilateral(img, ss, sc).view(np.uint32), ref2.view(np.uint32))
+
+
+# ---- the reference's own streaming over-segmentation (oracle/_ref/libref_results.so) ----
+
+import reference_cases as rc      # noqa: E402
+
+
+@pytest.mark.parametrize("case", sorted(rc.CASES))
+def test_oracle_matches_reference_golden(case):
+    """The oracle engine against digests of the REFERENCE's own per-frame results (tests/golden/reference_results.json,
+    written by tests/golden/make_reference_golden.py from the unmodified DenseSegmentation pipeline): every header
+    field, region id, scan interval, shape moment (float bits) and hierarchy-level-0 entry with neighbours."""
+    gold = json.load(open(os.path.join(GOLD, "reference_results.json")))[case]
+    clip, flows, opts = rc.load_case(case)
+    res = rc.run_stream(ob.OracleDense, clip, flows, opts)
+    assert len(res) == gold["frames"]
+    assert [int(r["region_id"].size) for r in res] == gold["regions_per_frame"]
+    assert rc.digest(res) == gold["sha256"]
+
+
+@pytest.mark.parametrize("case", sorted(rc.CASES))
+def test_oracle_equals_compiled_reference(case):
+    """Same cases, field by field against the compiled reference where oracle/_ref/libref_results.so exists, and the
+    committed digests against what the library produces now (guards the fixture against a stale library)."""
+    import reference_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref/libref_results.so not built (needs /root/reference)")
+    clip, flows, opts = rc.load_case(case)
+    ref = rc.run_stream(rb.ReferenceDense, clip, flows, opts)
+    assert rc.digest(ref) == json.load(open(os.path.join(GOLD, "reference_results.json")))[case]["sha256"]
+    assert rc.first_difference(ref, rc.run_stream(ob.OracleDense, clip, flows, opts)) is None
+    # the oracle's reference-style threading (parallel graph construction) must not change a bit either
+    if case in ("real_chunk8", "synth_flow"):
+        assert rc.first_difference(ref, rc.run_stream(ob.OracleDense, clip, flows, dict(opts, num_threads=4))) is None
