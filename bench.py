@@ -2,7 +2,7 @@
 """bench.py -- frames/s of dense video over-segmentation at 1920x1080 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W              # this repo (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...     # reference CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...     # the reference's own CPU path (oracle/_ref)
 
 A "step" is one chunk of the streaming hot path: 19 new 1080p frames pushed through the
 DenseSegmentationUnit mirror (preprocess -> edge build -> bucket sort -> merge -> labels / N4 /
@@ -14,8 +14,10 @@ RLE -> region bookkeeping), i.e. exactly what the reference outputs per chunk
             rasterisation runs / neighbour pairs back
   roofline: edge-build kernel, algorithmic bytes / CUDA-event time of its launches inside the
             timed region, against MEASURED_PEAKS.json's HBM copy bandwidth
-  cpu_baseline : the oracle (line-by-line port of the reference's CPU path, oracle/) timed on
-            the same box's host cores on a bounded sample (rank 0, N = 1 only)
+  cpu_baseline : the reference's own DenseSegmentation pipeline compiled unmodified into
+            oracle/_ref/libref_results.so (kind "reference"; the oracle port if that prebuilt
+            file is missing, kind "port") timed on the same box's host cores on a bounded sample
+            (rank 0, N = 1 only)
 Multi GPU (torchrun): frame-chunk groups of ONE synthetic video are sharded over the ranks
 (weak scaling, fixed frames per GPU); the only data-path exchange is the seam hand-over of the
 two overlap frames' region-id maps (NCCL send/recv over NVLink, C1) and the all-gather of the
@@ -87,19 +89,40 @@ def frame_index(k):
     return k if k < UNIQUE_FRAMES else period - k
 
 
+def cpu_engine():
+    """The CPU implementation of the path the CPU legs time: the reference's own DenseSegmentation pipeline
+    (oracle/_ref/libref_results.so, built from /root/reference where that is mounted and shipped as a prebuilt
+    file) or, without it, the oracle port.  Returns (kind, factory(w, h), threads)."""
+    import oracle_binding as ob
+    import reference_binding as rb
+    cores = os.cpu_count() or 1
+    ok = rb.available(build=False)
+    if ok:
+        try:
+            rb.lib()
+        except OSError as e:      # a prebuilt file this box cannot load: say so and time the port instead
+            print(f"bench: {rb.LIB_PATH} not loadable ({e}); timing the oracle port", file=sys.stderr)
+            ok = False
+    if ok:
+        # threads: the reference parallelises graph construction with one std::thread per frame
+        # (FLAGS_parallel_graph_construction) and the bilateral filter with OpenMP over 8 row blocks
+        return "reference", (lambda w, h: rb.ReferenceDense(w, h)), cores
+    return "port", (lambda w, h: ob.OracleDense(w, h, num_threads=cores)), cores
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the real
-    seg_tree_sample cannot be built in this image) on the box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path (its DenseSegmentation::ProcessFrame
+    stream compiled unmodified, oracle/Makefile; seg_tree_sample's decode / hierarchy / writer stages are outside the
+    path) on the box's host cores."""
     if rank != 0:
         return
-    import oracle_binding as ob
     from video_segment_b200.synth import synth
     w, h = args.width, args.height
-    cores = os.cpu_count() or 1
+    kind, make, cores = cpu_engine()
     nfr = args.ref_frames
     frames = list(synth(3, w, h, nfr))
     def one_step():
-        o = ob.OracleDense(w, h, num_threads=cores)
+        o = make(w, h)
         got = 0
         for f in frames:
             got += len(o.push(f))
@@ -121,7 +144,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{w}x{h} synthetic, dense over-seg only (BASELINE config 3 without the hierarchical stage)",
                    "step": sample, "threads": cores},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -286,10 +309,9 @@ def main():
         "merge_rounds_per_step": leg_dev["stats"]["merge_rounds"] / K,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle_binding as ob
-        cores = os.cpu_count() or 1
+        kind, make, cores = cpu_engine()
         nfr = 4
-        o = ob.OracleDense(w, h, num_threads=cores)
+        o = make(w, h)
         t0 = time.perf_counter()
         got = 0
         for f in host_frames[:nfr]:
@@ -297,7 +319,7 @@ def main():
         got += len(o.flush())
         dt = time.perf_counter() - t0
         o.close()
-        line["cpu_baseline"] = {"value": got / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+        line["cpu_baseline"] = {"value": got / dt, "unit": "frames/s", "cores": cores, "kind": kind,
                                 "sample": f"first {nfr} frames of the same clip segmented as one flushed chunk ({dt:.1f} s)"}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -17,6 +17,8 @@ CASES = {
     "real_chunk8": (("real", 24), None, dict(chunk_size=8)),
     "real_chunk5_overlap04": (("real", 14), None, dict(chunk_size=5, chunk_overlap_ratio=0.4)),
     "real_l1": (("real", 12), None, dict(chunk_size=8, color_distance=0)),
+    "real_l1_single_chunk_plain": (("real", 10), None, dict(color_distance=0, enforce_n4_connectivity=0, enforce_spatial_connectedness=0)),
+    "real_single_chunk": (("real", 12), None, dict()),
     "real_no_n4": (("real", 12), None, dict(chunk_size=8, enforce_n4_connectivity=0)),
     "real_no_connectedness": (("real", 12), None, dict(chunk_size=8, enforce_spatial_connectedness=0)),
     "real_no_presmoothing": (("real", 12), None, dict(chunk_size=8, presmoothing=0)),
