@@ -4,15 +4,17 @@
  * over-segmentation path (videosegmentation/video_segment @ c930c455).  Every
  * function cites the reference file:line it follows (paths relative to the
  * reference root).  PINNING: the reference ships no tests, golden vectors or
- * fixtures for this path and cannot be built in this
- * image (needs OpenCV 2.4 / FFmpeg 2.2 / gflags / boost / protobuf), but its
- * pixel distances, FastSegmentationGraph (the merge) and ColorHistogram compile
- * unmodified into oracle/_ref (Makefile target _ref, stand-ins in ref_shim/)
- * and tests/test_oracle_cpu.py holds this restatement bit-identical /
- * partition-identical to them.  Third-party arithmetic (cv::Mat::convertTo,
- * cv::copyMakeBorder, cv::minMaxLoc, 8-bit cv::cvtColor BGR2Lab) is pinned by
- * cv2 golden vectors (tests/golden/).  PARITY UNPINNED for the rest: bilateral
- * filter and result shaping (N4, RLE, tubes, ids, shape moments, proto).
+ * fixtures for this path and its executables cannot be
+ * built in this image (OpenCV 2.4 / FFmpeg 2.2 / glog / gflags / boost /
+ * protobuf are absent), but its over-segmentation library compiles UNMODIFIED
+ * into oracle/_ref against small stand-ins for those libraries (Makefile target
+ * _ref, oracle/ref_shim/): libref_results.so is the reference's whole
+ * DenseSegmentation::ProcessFrame stream, and tests/test_oracle_cpu.py holds this
+ * restatement identical to it in every field of every frame result (17 cases),
+ * plus the bilateral filter, the merge and the colour histogram in isolation.
+ * Reference-generated golden digests: tests/golden/reference_results.json.
+ * Third-party arithmetic (cv::Mat::convertTo, cv::copyMakeBorder, cv::minMaxLoc,
+ * 8-bit cv::cvtColor BGR2Lab) is pinned by cv2 golden vectors (tests/golden/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product
