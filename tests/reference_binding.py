@@ -88,3 +88,88 @@ class ReferenceDense:
             self.close()
         except Exception:
             pass
+
+
+# ---- the C++ host side (video_segment_b200/host/b200_dense_segmentation.*) through tests/host_check_wrap.cpp ----
+
+HOST_LIB_PATH = os.path.join(_ROOT, "oracle", "_ref", "libb200_host_check.so")
+_host = None
+
+
+def host_available(build: bool = True) -> bool:
+    available(build)
+    return os.path.exists(HOST_LIB_PATH) and os.path.exists(LIB_PATH)
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        L = C.CDLL(HOST_LIB_PATH)
+        L.host_check_desc_vs_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                                   C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.b200_dense_create.restype = C.c_void_p
+        L.b200_dense_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int]
+        L.b200_dense_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b200_dense_flush.argtypes = [C.c_void_p]
+        L.b200_dense_pop.argtypes = [C.c_void_p, C.c_void_p]
+        L.b200_dense_kernel_launches.argtypes = [C.c_void_p]
+        L.b200_dense_kernel_launches.restype = C.c_longlong
+        L.b200_dense_destroy.argtypes = [C.c_void_p]
+        _host = L
+    return _host
+
+
+def host_check_desc_vs_reference(clip, flows, **opts):
+    """(#frames whose rebuilt SegmentationDesc differs from the reference's own, first difference)."""
+    o = default_opts(**opts)
+    clip = np.ascontiguousarray(clip)
+    t, h, w, _ = clip.shape
+    fl = None if flows is None else np.ascontiguousarray(flows, np.float32)
+    msg = C.create_string_buffer(256)
+    bad = host_lib().host_check_desc_vs_reference(
+        clip.ctypes.data, None if fl is None else fl.ctypes.data, t, w, h, o.presmoothing, o.frac_min_region_size,
+        o.chunk_size, o.chunk_overlap_ratio, o.num_constraint_frames, o.enforce_n4_connectivity,
+        o.enforce_spatial_connectedness, o.color_distance, msg, 256)
+    return bad, msg.value.decode()
+
+
+class B200HostDense:
+    """segmentation::B200DenseSegmentation (the C++ host class over libvsb200.so) behind the OracleDense call shape.
+    Needs a B200: construction succeeds anywhere, the first push aborts without a device (no CPU fallback)."""
+
+    def __init__(self, width, height, use_flow=False, **opts):
+        self.w, self.h, self.use_flow = width, height, use_flow
+        o = default_opts(**opts)
+        self._h = host_lib().b200_dense_create(o.presmoothing, o.frac_min_region_size, o.chunk_size, o.chunk_overlap_ratio,
+                                               o.num_constraint_frames, o.enforce_n4_connectivity,
+                                               o.enforce_spatial_connectedness, o.color_distance, width, height, int(use_flow))
+        self._n = 0
+
+    def push(self, bgr, flow=None, pts=None):
+        bgr = np.ascontiguousarray(bgr)
+        fl = None
+        if self.use_flow and self._n > 0:
+            fl = np.ascontiguousarray(flow, np.float32)
+        n = host_lib().b200_dense_push(self._h, bgr.ctypes.data, self.w * 3, None if fl is None else fl.ctypes.data, self.w * 8)
+        self._n += 1
+        return self._pop(n)
+
+    def flush(self):
+        return self._pop(host_lib().b200_dense_flush(self._h))
+
+    def kernel_launches(self):
+        return int(host_lib().b200_dense_kernel_launches(self._h))
+
+    def _pop(self, n):
+        out = []
+        for _ in range(n):
+            r = FrameResult()
+            assert host_lib().b200_dense_pop(self._h, C.byref(r)) == 0
+            out.append(result_to_dict(r))
+        return out
+
+    def close(self):
+        if self._h:
+            host_lib().b200_dense_destroy(self._h)
+            self._h = None

@@ -426,3 +426,16 @@ def test_oracle_equals_compiled_reference(case):
     # the oracle's reference-style threading (parallel graph construction) must not change a bit either
     if case in ("real_chunk8", "synth_flow"):
         assert rc.first_difference(ref, rc.run_stream(ob.OracleDense, clip, flows, dict(opts, num_threads=4))) is None
+
+
+@pytest.mark.parametrize("case", ["real_chunk8", "real_l1_single_chunk_plain", "synth_flow", "synth_one_frame"])
+def test_cpp_host_side_rebuilds_reference_messages(case):
+    """video_segment_b200/host: FrameResultToSegmentationDesc (the C++ host side's array -> protobuf step, compiled
+    against the reference's own headers) applied to the flattened results of the compiled reference reproduces the
+    reference's SegmentationDesc objects exactly, values and presence bits."""
+    import reference_binding as rb
+    if not rb.host_available():
+        pytest.skip("oracle/_ref/libb200_host_check.so not built (needs /root/reference)")
+    clip, flows, opts = rc.load_case(case)
+    bad, msg = rb.host_check_desc_vs_reference(clip, flows, **opts)
+    assert bad == 0, msg
