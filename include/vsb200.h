@@ -186,6 +186,43 @@ int vsb200_region_hist_finish(const void* dev_scratch, int n_regions, int lum_bi
 int vsb200_hist_chisquare(const float* dev_hist, int total_bins, const int32_t* dev_pairs, int n_pairs,
                           float* dev_out, void* stream);
 
+/* ---- result container (csrc/pb_io.cpp, host only) ----
+ * The reference's segmentation file, segment_util/segmentation_io.cpp: "HEAD" int32 n, n x int32 | per chunk "CHNK"
+ * int32 chunk_id, int32 n_frames, n x int64 absolute frame offsets, n x int64 pts, int64 offset of the next header,
+ * then per frame "SEGD" int32 size, bytes | "TERM" int32 n_chunks.  Byte identical to SegmentationWriter for the
+ * same sequence of calls.  Frame payloads are opaque: the proto2 wire bytes of vsb200_dense_last_proto, or the
+ * stripped format below. */
+typedef struct vsb200_seg_writer vsb200_seg_writer;
+/* SegmentationWriter::OpenFile(header_entries) (segmentation_io.cpp:46-71); SegmentationWriterUnit passes {1, 0}
+ * (segmentation_unit.cpp:366-369). */
+int vsb200_seg_writer_open(const char* filename, const int32_t* header_entries, int n_entries, vsb200_seg_writer** out);
+/* SegmentationWriter::AddSegmentationDataToChunk(data, pts) (:80-88). */
+int vsb200_seg_writer_add(vsb200_seg_writer*, const uint8_t* data, size_t size, int64_t pts);
+/* SegmentationWriter::AddSegmentationToChunk(desc, pts) (:73-78) for the frame most recently popped from `dense`:
+ * its SegmentationDesc is serialised straight from the result arrays, no message objects in between. */
+int vsb200_seg_writer_add_last_frame(vsb200_seg_writer*, vsb200_dense* dense, int64_t pts);
+/* SegmentationWriter::WriteChunk (:90-143). */
+int vsb200_seg_writer_write_chunk(vsb200_seg_writer*);
+/* SegmentationWriter::WriteTermHeaderAndClose (:145-155): writes the pending chunk, "TERM", closes and frees. */
+int vsb200_seg_writer_close(vsb200_seg_writer*);
+
+typedef struct vsb200_seg_reader vsb200_seg_reader;
+/* SegmentationReader::OpenFileAndReadHeaders (:166-229): walks the chunk headers, collects offsets and pts. */
+int vsb200_seg_reader_open(const char* filename, vsb200_seg_reader** out);
+int vsb200_seg_reader_num_frames(const vsb200_seg_reader*);
+int vsb200_seg_reader_num_header_flags(const vsb200_seg_reader*);
+const int32_t* vsb200_seg_reader_header_flags(const vsb200_seg_reader*);
+const int64_t* vsb200_seg_reader_time_stamps(const vsb200_seg_reader*);
+/* SeekToFrame + ReadNextFrameBinary (:253-274): returns the payload size of `frame`, copying min(size, cap) bytes;
+ * 0 on a parse error. */
+size_t vsb200_seg_reader_read(vsb200_seg_reader*, int frame, uint8_t* buf, size_t cap);
+void vsb200_seg_reader_close(vsb200_seg_reader*);
+
+/* StripToEssentials(desc, save_vectorization = false, save_shape_moments, &binary) (segmentation_io.cpp:311-443) from
+ * the arrays of a frame result: returns the size, copying min(size, cap) bytes.  The vectorised variant the writer
+ * unit uses needs compute_vectorization (not built). */
+size_t vsb200_strip_to_essentials(const vsb200_frame_result* r, int save_shape_moments, uint8_t* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 // segmentation.proto:55-172.  In-memory only: no wire format here (the wire encoder under test is the product's own).
 #ifndef VSO_REF_SHIM_SEGMENTATION_PB_H_
 #define VSO_REF_SHIM_SEGMENTATION_PB_H_
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <utility>
@@ -182,6 +183,11 @@ class SegmentationDesc {
   VSO_PB_MSG(SegmentationDesc_VectorMesh, vector_mesh)
   VSO_PB_SCALAR(SegmentationDesc_Connectedness, connectedness, SegmentationDesc_Connectedness_N4_CONNECT)
   VSO_PB_SCALAR(bool, rasterization_removed, false)
+ public:
+  // No wire format in this stand-in (header comment): the reference's file IO is exercised through its byte-level
+  // entry points (AddSegmentationDataToChunk / ReadNextFrameBinary); the message-level ones abort if reached.
+  bool SerializeToString(std::string*) const { std::abort(); }
+  bool ParseFromString(const std::string&) { std::abort(); }
 };
 
 }  // namespace segmentation

@@ -3,6 +3,8 @@
 // reference (oracle/_ref/libref_results.so):
 //   * host_check_desc_vs_reference: the reference's OWN SegmentationDesc objects against the ones
 //     FrameResultToSegmentationDesc rebuilds from the flat result arrays -- values and presence bits (CPU test);
+//   * ref_io_*: the reference's own SegmentationWriter / SegmentationReader / StripToEssentials
+//     (segment_util/segmentation_io.cpp, unmodified) for byte-for-byte checks of csrc/pb_io.cu (CPU test);
 //   * b200_dense_*: the call shape of ref_dense_* (oracle/ref_results_wrap.cpp) over B200DenseSegmentation (GPU test).
 #include <stdint.h>
 #include <string.h>
@@ -17,6 +19,7 @@
 
 #include "b200_dense_segmentation.h"
 #include "ref_flatten.hpp"
+#include "segment_util/segmentation_io.h"
 #include "segmentation/dense_segmentation.h"
 
 namespace {
@@ -137,6 +140,56 @@ int host_check_desc_vs_reference(const uint8_t* frames, const float* flows, int 
     msg[msg_cap - 1] = 0;
   }
   return seen == t ? bad : -1;
+}
+
+// SegmentationWriter over opaque frame payloads: HEAD with `entries`, AddSegmentationDataToChunk per frame, WriteChunk
+// after every `chunk_every` frames (0: never), WriteTermHeaderAndClose.
+int ref_io_write(const char* filename, const int32_t* entries, int n_entries, const uint8_t* blob, const int64_t* sizes,
+                 const int64_t* pts, int n_frames, int chunk_every) {
+  segmentation::SegmentationWriter w(filename);
+  if (!w.OpenFile(std::vector<int>(entries, entries + n_entries))) return -1;
+  size_t pos = 0;
+  for (int k = 0; k < n_frames; ++k) {
+    w.AddSegmentationDataToChunk(std::string((const char*)blob + pos, (size_t)sizes[k]), pts[k]);
+    pos += (size_t)sizes[k];
+    if (chunk_every > 0 && (k + 1) % chunk_every == 0) w.WriteChunk();
+  }
+  w.WriteTermHeaderAndClose();
+  return 0;
+}
+
+// SegmentationReader: frame count, then per frame pts and payload (concatenated into blob, sizes out).
+int ref_io_read(const char* filename, int32_t* flags, int flags_cap, int* n_flags, uint8_t* blob, size_t blob_cap, int64_t* sizes,
+                int64_t* pts, int frames_cap) {
+  segmentation::SegmentationReader r(filename);
+  if (!r.OpenFileAndReadHeaders()) return -1;
+  *n_flags = (int)r.GetHeaderFlags().size();
+  for (int i = 0; i < *n_flags && i < flags_cap; ++i) flags[i] = r.GetHeaderFlags()[i];
+  const int n = r.NumFrames();
+  size_t pos = 0;
+  for (int k = 0; k < n && k < frames_cap; ++k) {
+    std::string data;
+    r.SeekToFrame(k);
+    if (!r.ReadNextFrameBinary(&data)) return -1;
+    if (pos + data.size() > blob_cap) return -1;
+    memcpy(blob + pos, data.data(), data.size());
+    pos += data.size();
+    sizes[k] = (int64_t)data.size();
+    pts[k] = r.TimeStamps()[k];
+  }
+  return n;
+}
+
+// StripToEssentials(desc, false, save_shape_moments) on the message FrameResultToSegmentationDesc builds from `r`.
+long long ref_io_strip(const RefFrameResult* r, int save_shape_moments, uint8_t* buf, size_t cap) {
+  vsb200_frame_result fr;
+  memcpy(&fr, r, sizeof(fr));
+  SegmentationDesc desc;
+  segmentation::FrameResultToSegmentationDesc(fr, &desc);
+  std::string out;
+  segmentation::StripToEssentials(desc, false, save_shape_moments != 0, &out);
+  if (buf && cap) memcpy(buf, out.data(), out.size() < cap ? out.size() : cap);
+  return (long long)out.size();
 }
 
 void* b200_dense_create(int presmoothing, float frac_min_region_size, int chunk_size, float chunk_overlap_ratio, int num_constraint_frames,

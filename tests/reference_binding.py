@@ -173,3 +173,67 @@ class B200HostDense:
         if self._h:
             host_lib().b200_dense_destroy(self._h)
             self._h = None
+
+
+# ---- the reference's own SegmentationWriter / SegmentationReader / StripToEssentials (segmentation_io.cpp) ----
+
+def _io_lib():
+    L = host_lib()
+    if not getattr(L, "_io_ready", False):
+        L.ref_io_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ref_io_read.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.c_void_p,
+                                  C.c_void_p, C.c_int]
+        L.ref_io_strip.argtypes = [C.POINTER(FrameResult), C.c_int, C.c_void_p, C.c_size_t]
+        L.ref_io_strip.restype = C.c_longlong
+        L._io_ready = True
+    return L
+
+
+def ref_io_write(filename, header_entries, payloads, pts, chunk_every=0):
+    ent = np.asarray(header_entries, np.int32)
+    sizes = np.asarray([len(p) for p in payloads], np.int64)
+    ts = np.asarray(pts, np.int64)
+    blob = b"".join(payloads)
+    rc = _io_lib().ref_io_write(filename.encode(), ent.ctypes.data, len(ent), blob, sizes.ctypes.data, ts.ctypes.data,
+                                len(payloads), chunk_every)
+    assert rc == 0
+
+
+def ref_io_read(filename, max_frames=4096, max_bytes=1 << 26):
+    flags = np.zeros(64, np.int32)
+    nf = C.c_int()
+    blob = np.zeros(max_bytes, np.uint8)
+    sizes = np.zeros(max_frames, np.int64)
+    ts = np.zeros(max_frames, np.int64)
+    n = _io_lib().ref_io_read(filename.encode(), flags.ctypes.data, 64, C.byref(nf), blob.ctypes.data, max_bytes,
+                              sizes.ctypes.data, ts.ctypes.data, max_frames)
+    assert n >= 0
+    out, pos = [], 0
+    for k in range(n):
+        out.append(blob[pos:pos + sizes[k]].tobytes())
+        pos += int(sizes[k])
+    return flags[:nf.value].tolist(), out, ts[:n].tolist()
+
+
+def result_struct(d: dict):
+    """A FrameResult structure over the arrays of a result dict (keeps them alive through ._keep)."""
+    r = FrameResult()
+    for k in ("width", "height", "chunk_id", "chunk_size", "overlap_start", "hierarchy_frame_idx", "connectedness"):
+        setattr(r, k, int(d[k]))
+    keep = {k: np.ascontiguousarray(d[k], np.float32 if k == "shape_moments" else np.int32)
+            for k in ("region_id", "interval_offset", "intervals", "shape_moments", "compound", "neighbor_offset", "neighbor_id")}
+    r.n_regions = len(keep["region_id"])
+    r.n_compound = len(keep["compound"])
+    for k, a in keep.items():
+        setattr(r, k, a.ctypes.data_as(C.POINTER(C.c_float if k == "shape_moments" else C.c_int32)))
+    r.pts = int(d.get("pts", 0))
+    r._keep = keep
+    return r
+
+
+def ref_io_strip(d: dict, save_shape_moments: bool) -> bytes:
+    r = result_struct(d)
+    n = _io_lib().ref_io_strip(C.byref(r), int(save_shape_moments), None, 0)
+    buf = C.create_string_buffer(max(1, n))
+    _io_lib().ref_io_strip(C.byref(r), int(save_shape_moments), buf, n)
+    return buf.raw[:n]

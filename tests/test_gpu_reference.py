@@ -61,3 +61,38 @@ def test_cpp_host_class_matches_compiled_reference():
     e.close()
     assert launches > 0
     assert rc.first_difference(ref, got) is None
+
+
+def test_segmentation_file_written_from_the_engine(tmp_path, real_clip):
+    """Result container (csrc/pb_io.cu): frames appended from the engine's wire encoder as they are popped; the file
+    read back holds exactly the per-frame protobuf bytes and pts, and the reference's own reader (where shipped)
+    reads the same."""
+    from proto_schema import segmentation_desc_class
+    from video_segment_b200.segio import SegmentationReader, SegmentationWriter
+    from video_segment_b200.unit import DenseSegmentationUnit
+    clip = real_clip[:8]
+    h, w = clip[0].shape[:2]
+    path = str(tmp_path / "seg.pb")
+    writer = SegmentationWriter(path)
+    assert writer.open_file([1, 0])
+    u = DenseSegmentationUnit(want_proto=True)
+    u.segmentation_writer = writer
+    assert u.open_streams(w, h)
+    got = []
+    for k, f in enumerate(clip):
+        got += u.process_frame(f, pts=1000 * k)
+    got += u.post_process()
+    u.close()
+    writer.write_term_header_and_close()
+    r = SegmentationReader(path)
+    assert r.open_file_and_read_headers()
+    assert r.get_header_flags() == [1, 0] and r.num_frames() == len(clip)
+    assert r.time_stamps() == [1000 * k for k in range(len(clip))]
+    frames = [r.read_next_frame_binary() for _ in range(len(clip))]
+    r.close_file()
+    assert frames == [g["proto"] for g in got]
+    m = segmentation_desc_class()()
+    m.ParseFromString(frames[0])
+    assert m.frame_width == w and m.frame_height == h and [x.id for x in m.region] == list(got[0]["region_id"])
+    if rb.host_available(build=False):
+        assert rb.ref_io_read(path) == ([1, 0], frames, [1000 * k for k in range(len(clip))])

@@ -49,6 +49,10 @@ EXPORTED_SYMBOLS = [
     "vsb200_bucket_index", "vsb200_sort_edges", "vsb200_sort_scratch_bytes", "vsb200_segment_chunk",
     "vsb200_bgr2lab", "vsb200_region_hist_scratch_bytes", "vsb200_region_hist_reset", "vsb200_region_hist_add",
     "vsb200_region_hist_finish", "vsb200_hist_chisquare",
+    "vsb200_seg_writer_open", "vsb200_seg_writer_add", "vsb200_seg_writer_add_last_frame", "vsb200_seg_writer_write_chunk",
+    "vsb200_seg_writer_close", "vsb200_seg_reader_open", "vsb200_seg_reader_num_frames", "vsb200_seg_reader_num_header_flags",
+    "vsb200_seg_reader_header_flags", "vsb200_seg_reader_time_stamps", "vsb200_seg_reader_read", "vsb200_seg_reader_close",
+    "vsb200_strip_to_essentials",
 ]
 
 _lib = None
@@ -95,6 +99,19 @@ def lib() -> C.CDLL:
         "vsb200_region_hist_add": ([vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
         "vsb200_region_hist_finish": ([vp, C.c_int, C.c_int, C.c_int, vp, vp, vp], C.c_int),
         "vsb200_hist_chisquare": ([vp, C.c_int, vp, C.c_int, vp, vp], C.c_int),
+        "vsb200_seg_writer_open": ([C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(vp)], C.c_int),
+        "vsb200_seg_writer_add": ([vp, C.c_char_p, C.c_size_t, C.c_int64], C.c_int),
+        "vsb200_seg_writer_add_last_frame": ([vp, vp, C.c_int64], C.c_int),
+        "vsb200_seg_writer_write_chunk": ([vp], C.c_int),
+        "vsb200_seg_writer_close": ([vp], C.c_int),
+        "vsb200_seg_reader_open": ([C.c_char_p, C.POINTER(vp)], C.c_int),
+        "vsb200_seg_reader_num_frames": ([vp], C.c_int),
+        "vsb200_seg_reader_num_header_flags": ([vp], C.c_int),
+        "vsb200_seg_reader_header_flags": ([vp], C.POINTER(C.c_int32)),
+        "vsb200_seg_reader_time_stamps": ([vp], C.POINTER(C.c_int64)),
+        "vsb200_seg_reader_read": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
+        "vsb200_seg_reader_close": ([vp], None),
+        "vsb200_strip_to_essentials": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
     }
     missing = []
     for name, (argtypes, restype) in sigs.items():

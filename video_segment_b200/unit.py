@@ -89,6 +89,9 @@ class DenseSegmentationUnit:
         self.want_id_maps = want_id_maps
         self._imported = False
         self.want_proto = want_proto
+        # optional segio.SegmentationWriter: every output frame is appended to its current chunk as it is popped, which
+        # is what a SegmentationWriterUnit placed behind this unit does (segmentation_unit.cpp:373-410)
+        self.segmentation_writer = None
         self._h = C.c_void_p()
         self.frame_width = self.frame_height = 0
         self.input_frames = self.output_frames = 0
@@ -139,6 +142,8 @@ class DenseSegmentationUnit:
                 buf = (C.c_uint8 * nb)()
                 lib().vsb200_dense_last_proto(self._h, buf, nb)
                 d["proto"] = bytes(buf)
+            if self.segmentation_writer is not None:
+                self.segmentation_writer.add_segmentation_to_chunk(self, r.pts)
             out.append(d)
             self.output_frames += 1
         if n:
