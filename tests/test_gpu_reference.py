@@ -43,26 +43,6 @@ def test_stream_matches_compiled_reference(case):
         assert np.array_equal(got[0]["neighbor_id"], ref[0]["neighbor_id"])
 
 
-def test_cpp_host_class_matches_compiled_reference():
-    """segmentation::B200DenseSegmentation (video_segment_b200/host: the C++ class with DenseSegmentation's ProcessFrame
-    signature over the C ABI, compiled against the reference's headers) on a flushed single chunk: the
-    SegmentationDesc objects it returns equal the reference's in every field."""
-    if not rb.host_available(build=False):
-        pytest.skip("oracle/_ref/libb200_host_check.so not shipped")
-    clip, flows, opts = rc.load_case("real_single_chunk")
-    ref = rc.run_stream(rb.ReferenceDense, clip, flows, opts)
-    h, w = clip[0].shape[:2]
-    e = rb.B200HostDense(w, h, **opts)
-    got = []
-    for f in clip:
-        got += e.push(f)
-    got += e.flush()
-    launches = e.kernel_launches()
-    e.close()
-    assert launches > 0
-    assert rc.first_difference(ref, got) is None
-
-
 def test_segmentation_file_written_from_the_engine(tmp_path, real_clip):
     """Result container (csrc/pb_io.cu): frames appended from the engine's wire encoder as they are popped; the file
     read back holds exactly the per-frame protobuf bytes and pts, and the reference's own reader (where shipped)
@@ -96,3 +76,23 @@ def test_segmentation_file_written_from_the_engine(tmp_path, real_clip):
     assert m.frame_width == w and m.frame_height == h and [x.id for x in m.region] == list(got[0]["region_id"])
     if rb.host_available(build=False):
         assert rb.ref_io_read(path) == ([1, 0], frames, [1000 * k for k in range(len(clip))])
+
+
+def test_cpp_host_class_matches_compiled_reference():
+    """segmentation::B200DenseSegmentation (video_segment_b200/host: the C++ class with DenseSegmentation's ProcessFrame
+    signature over the C ABI, compiled against the reference's headers) on a flushed single chunk: the
+    SegmentationDesc objects it returns equal the reference's in every field."""
+    if not rb.host_available(build=False):
+        pytest.skip("oracle/_ref/libb200_host_check.so not shipped")
+    clip, flows, opts = rc.load_case("real_single_chunk")
+    ref = rc.run_stream(rb.ReferenceDense, clip, flows, opts)
+    h, w = clip[0].shape[:2]
+    e = rb.B200HostDense(w, h, **opts)
+    got = []
+    for f in clip:
+        got += e.push(f)
+    got += e.flush()
+    launches = e.kernel_launches()
+    e.close()
+    assert launches > 0
+    assert rc.first_difference(ref, got) is None
