@@ -4,20 +4,43 @@
 // message, LOG / DLOG / VLOG swallow their stream.
 #ifndef VSO_REF_SHIM_GLOG_LOGGING_H_
 #define VSO_REF_SHIM_GLOG_LOGGING_H_
+#include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
+#include <string>
 
 namespace vso_shim {
 struct NullStream {
   template <class T> NullStream& operator<<(const T&) { return *this; }
   NullStream& operator<<(std::ostream& (*)(std::ostream&)) { return *this; }
 };
+// Formats with snprintf, not iostreams: the image's g++ links libstdc++ statically into every shared object, and the
+// locale facets of a second copy are not reliably initialised in a process that already loaded another one (numpy
+// loads the shared libstdc++ first), so `ostream << int` can crash exactly when a CHECK wants to report.
 struct FatalStream {
-  std::ostringstream s;
-  FatalStream(const char* file, int line, const char* what) { s << file << ":" << line << " check failed: " << what << " "; }
-  template <class T> FatalStream& operator<<(const T& v) { s << v; return *this; }
-  ~FatalStream() { std::cerr << s.str() << std::endl; std::abort(); }
+  std::string s;
+  FatalStream(const char* file, int line, const char* what) {
+    char b[64];
+    snprintf(b, sizeof(b), ":%d check failed: ", line);
+    s = std::string(file) + b + what + " ";
+  }
+  FatalStream& operator<<(const char* v) { s += v ? v : "(null)"; return *this; }
+  FatalStream& operator<<(const std::string& v) { s += v; return *this; }
+  FatalStream& operator<<(char v) { s += v; return *this; }
+  FatalStream& operator<<(bool v) { s += v ? "true" : "false"; return *this; }
+  FatalStream& operator<<(double v) { char b[64]; snprintf(b, sizeof(b), "%g", v); s += b; return *this; }
+  FatalStream& operator<<(float v) { return *this << (double)v; }
+  FatalStream& operator<<(long long v) { char b[32]; snprintf(b, sizeof(b), "%lld", v); s += b; return *this; }
+  FatalStream& operator<<(unsigned long long v) { char b[32]; snprintf(b, sizeof(b), "%llu", v); s += b; return *this; }
+  FatalStream& operator<<(int v) { return *this << (long long)v; }
+  FatalStream& operator<<(long v) { return *this << (long long)v; }
+  FatalStream& operator<<(unsigned v) { return *this << (unsigned long long)v; }
+  FatalStream& operator<<(unsigned long v) { return *this << (unsigned long long)v; }
+  FatalStream& operator<<(const void* v) { char b[32]; snprintf(b, sizeof(b), "%p", v); s += b; return *this; }
+  // anything else (cv::Size ...): through a local stream
+  template <class T> FatalStream& operator<<(const T& v) { std::ostringstream o; o << v; s += o.str(); return *this; }
+  ~FatalStream() { fputs(s.c_str(), stderr); fputc('\n', stderr); fflush(stderr); std::abort(); }
 };
 struct Voidify { void operator&(const NullStream&) {} void operator&(const FatalStream&) {} };
 }  // namespace vso_shim

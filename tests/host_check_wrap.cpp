@@ -30,15 +30,15 @@ static_assert(sizeof(RefFrameResult) == sizeof(vsb200_frame_result), "frame resu
 
 // First difference between two messages, values and has_ bits ("" if none).
 std::string DescDifference(const SegmentationDesc& a, const SegmentationDesc& b) {
-  std::ostringstream o;
-#define SAME(expr) if (!((a.expr) == (b.expr))) { o << #expr; return o.str(); }
+  // (std::string, not a stream: see the note on FatalStream in oracle/ref_shim/glog/logging.h)
+#define SAME(expr) if (!((a.expr) == (b.expr))) return std::string(#expr);
   SAME(has_frame_width()) SAME(frame_width()) SAME(has_frame_height()) SAME(frame_height())
   SAME(has_chunk_size()) SAME(chunk_size()) SAME(has_overlap_start()) SAME(overlap_start())
   SAME(has_chunk_id()) SAME(chunk_id()) SAME(has_hierarchy_frame_idx()) SAME(hierarchy_frame_idx())
   SAME(has_connectedness()) SAME(connectedness()) SAME(has_rasterization_removed()) SAME(has_vector_mesh())
   SAME(features_size()) SAME(region_size()) SAME(hierarchy_size())
 #undef SAME
-#define SAME(expr) if (!((x.expr) == (y.expr))) { o << what << " " << k << ": " #expr; return o.str(); }
+#define SAME(expr) if (!((x.expr) == (y.expr))) return std::string(what) + " " + std::to_string(k) + ": " #expr;
   const char* what = "region";
   for (int k = 0; k < a.region_size(); ++k) {
     const auto& x = a.region(k);
@@ -56,7 +56,7 @@ std::string DescDifference(const SegmentationDesc& a, const SegmentationDesc& b)
   }
   what = "compound";
   for (int l = 0; l < a.hierarchy_size(); ++l) {
-    if (a.hierarchy(l).region_size() != b.hierarchy(l).region_size()) { o << "hierarchy " << l << " size"; return o.str(); }
+    if (a.hierarchy(l).region_size() != b.hierarchy(l).region_size()) return "hierarchy " + std::to_string(l) + " size";
     for (int k = 0; k < a.hierarchy(l).region_size(); ++k) {
       const auto& x = a.hierarchy(l).region(k);
       const auto& y = b.hierarchy(l).region(k);
