@@ -237,3 +237,13 @@ def ref_io_strip(d: dict, save_shape_moments: bool) -> bytes:
     buf = C.create_string_buffer(max(1, n))
     _io_lib().ref_io_strip(C.byref(r), int(save_shape_moments), buf, n)
     return buf.raw[:n]
+
+
+def host_shape_check(seed: int, n_cases: int):
+    """(#mismatches, first mismatch) of csrc/host_shape.hpp against the reference's segmentation_util.cpp functions on
+    random rasters (tests/host_shape_check.cpp)."""
+    L = host_lib()
+    L.host_shape_check.argtypes = [C.c_uint, C.c_int, C.c_char_p, C.c_int]
+    msg = C.create_string_buffer(256)
+    bad = L.host_shape_check(seed, n_cases, msg, 256)
+    return bad, msg.value.decode()
