@@ -100,6 +100,10 @@ const int32_t* vsb200_dense_last_id_map(vsb200_dense*);
  * message (proto2 wire format, segment_util/segmentation.proto:55-172).  Returns the
  * byte count; copies at most cap bytes into buf. */
 size_t vsb200_dense_last_proto(vsb200_dense*, uint8_t* buf, size_t cap);
+/* The same encoder over caller-held result arrays (host only): protobuf's canonical serialisation of the frame's
+ * SegmentationDesc, what SerializeToString writes (segment_util/segmentation_io.cpp:73-78).  Returns the size,
+ * copying min(size, cap) bytes. */
+size_t vsb200_encode_frame_proto(const vsb200_frame_result* r, uint8_t* buf, size_t cap);
 /* Per-stage device/host milliseconds accumulated since creation:
  * [0] h2d+preprocess [1] edge build [2] sort [3] merge [4] labels+n4+rle [5] host shaping
  * [6] neighbours; and counters [7] kernels launched [8] merge rounds. */

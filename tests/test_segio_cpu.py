@@ -115,3 +115,58 @@ def test_strip_to_essentials_matches_reference(moments):
         assert mine == rb.ref_io_strip(d, moments)
         w, h, nreg = struct.unpack_from("<iii", mine, 0)
         assert (w, h, nreg) == (d["width"], d["height"], len(d["region_id"]))
+
+
+def _message_from_result(Desc, d):
+    """The SegmentationDesc protobuf (real protobuf runtime, schema restated in tests/proto_schema.py) holding the fields
+    RetrieveSegmentation3D / SegmentAndOutputChunk set for a frame (segmentation.cpp:458-533, dense_segmentation.cpp:385-387)."""
+    m = Desc()
+    m.frame_width, m.frame_height, m.chunk_id = d["width"], d["height"], d["chunk_id"]
+    m.connectedness = d["connectedness"]
+    m.chunk_size, m.overlap_start, m.hierarchy_frame_idx = d["chunk_size"], d["overlap_start"], d["hierarchy_frame_idx"]
+    off = d["interval_offset"]
+    for k, rid in enumerate(d["region_id"]):
+        r = m.region.add()
+        r.id = int(rid)
+        r.raster.SetInParent()
+        for y, lx, rx in d["intervals"][off[k]:off[k + 1]]:
+            s = r.raster.scan_inter.add()
+            s.y, s.left_x, s.right_x = int(y), int(lx), int(rx)
+        sm = d["shape_moments"][k]
+        r.shape_moments.size, r.shape_moments.mean_x, r.shape_moments.mean_y = float(sm[0]), float(sm[1]), float(sm[2])
+        r.shape_moments.moment_xx, r.shape_moments.moment_xy, r.shape_moments.moment_yy = float(sm[3]), float(sm[4]), float(sm[5])
+    if len(d["compound"]):
+        h = m.hierarchy.add()
+        no = d["neighbor_offset"]
+        for k, (cid, size, start, end) in enumerate(d["compound"]):
+            c = h.region.add()
+            c.id, c.size, c.start_frame, c.end_frame = int(cid), int(size), int(start), int(end)
+            c.neighbor_id.extend(int(x) for x in d["neighbor_id"][no[k]:no[k + 1]])
+    return m
+
+
+@pytest.mark.parametrize("case", ["real_chunk8", "synth_flow", "synth_one_frame"])
+def test_wire_encoder_equals_protobuf_serialisation(case, tmp_path):
+    """vsb200_encode_frame_proto (the engine's wire encoder, host code) writes exactly the bytes the protobuf runtime
+    serialises for the same SegmentationDesc, on whole oracle streams (= the reference's messages, test_oracle_cpu);
+    a file of such frames parses back to the same messages."""
+    from proto_schema import segmentation_desc_class
+    from video_segment_b200.segio import encode_frame_proto
+    Desc = segmentation_desc_class()
+    clip, flows, opts = rc.load_case(case)
+    res = rc.run_stream(ob.OracleDense, clip, flows, opts)
+    path = str(tmp_path / "stream.pb")
+    w = SegmentationWriter(path)
+    assert w.open_file([1, 0])
+    want = []
+    for k, d in enumerate(res):
+        mine = encode_frame_proto(rb.result_struct(d))
+        m = _message_from_result(Desc, d)
+        assert mine == m.SerializeToString(deterministic=True), (case, k)
+        back = Desc()
+        back.ParseFromString(mine)
+        assert back == m
+        w.add_segmentation_data_to_chunk(mine, 40 * k)
+        want.append(mine)
+    w.write_term_header_and_close()
+    assert _read(path) == ([1, 0], want, [40 * k for k in range(len(res))])

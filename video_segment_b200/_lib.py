@@ -52,7 +52,7 @@ EXPORTED_SYMBOLS = [
     "vsb200_seg_writer_open", "vsb200_seg_writer_add", "vsb200_seg_writer_add_last_frame", "vsb200_seg_writer_write_chunk",
     "vsb200_seg_writer_close", "vsb200_seg_reader_open", "vsb200_seg_reader_num_frames", "vsb200_seg_reader_num_header_flags",
     "vsb200_seg_reader_header_flags", "vsb200_seg_reader_time_stamps", "vsb200_seg_reader_read", "vsb200_seg_reader_close",
-    "vsb200_strip_to_essentials",
+    "vsb200_strip_to_essentials", "vsb200_encode_frame_proto",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         "vsb200_seg_reader_read": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
         "vsb200_seg_reader_close": ([vp], None),
         "vsb200_strip_to_essentials": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
+        "vsb200_encode_frame_proto": ([vp, vp, C.c_size_t], C.c_size_t),
     }
     missing = []
     for name, (argtypes, restype) in sigs.items():

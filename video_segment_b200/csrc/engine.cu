@@ -976,6 +976,33 @@ size_t vsb200_dense_last_proto(vsb200_dense* d, uint8_t* buf, size_t cap) {
   return d->proto_buf.size();
 }
 
+// Host only: the same encoder over caller-held arrays (a frame result kept after later pops, or one rebuilt from a
+// file).  Bytes are protobuf's canonical serialisation of the message (fields in field-number order, unpacked
+// repeated int32), i.e. what SegmentationDesc::SerializeToString writes (segmentation_io.cpp:73-78).
+size_t vsb200_encode_frame_proto(const vsb200_frame_result* r, uint8_t* buf, size_t cap) {
+  if (!r || r->n_regions < 0 || r->n_compound < 0) return 0;
+  FrameOut f;
+  f.width = r->width; f.height = r->height; f.chunk_id = r->chunk_id; f.chunk_size = r->chunk_size;
+  f.overlap_start = r->overlap_start; f.hierarchy_frame_idx = r->hierarchy_frame_idx; f.connectedness = r->connectedness;
+  f.pts = r->pts;
+  const int nr = r->n_regions, nc = r->n_compound;
+  if (nr > 0) {
+    f.region_id.assign(r->region_id, r->region_id + nr);
+    f.interval_offset.assign(r->interval_offset, r->interval_offset + nr + 1);
+    f.intervals.assign(r->intervals, r->intervals + 3 * (size_t)r->interval_offset[nr]);
+    f.moments.assign(r->shape_moments, r->shape_moments + 6 * (size_t)nr);
+  }
+  if (nc > 0) {
+    f.compound.assign(r->compound, r->compound + 4 * (size_t)nc);
+    f.neighbor_offset.assign(r->neighbor_offset, r->neighbor_offset + nc + 1);
+    f.neighbor_id.assign(r->neighbor_id, r->neighbor_id + r->neighbor_offset[nc]);
+  }
+  std::vector<uint8_t> out;
+  encode_proto(f, &out);
+  if (buf && cap) memcpy(buf, out.data(), std::min(cap, out.size()));
+  return out.size();
+}
+
 void vsb200_dense_stats(vsb200_dense* d, double out[9]) {
   if (d && out) memcpy(out, d->stats, sizeof(double) * 9);
 }

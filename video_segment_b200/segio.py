@@ -103,3 +103,11 @@ def strip_to_essentials(result: FrameResult, save_shape_moments: bool = False) -
     buf = C.create_string_buffer(max(1, n))
     lib().vsb200_strip_to_essentials(C.byref(result), int(save_shape_moments), buf, n)
     return buf.raw[:n]
+
+
+def encode_frame_proto(result: FrameResult) -> bytes:
+    """Wire bytes of the frame's SegmentationDesc (== SegmentationDesc::SerializeToString) from a frame result."""
+    n = lib().vsb200_encode_frame_proto(C.byref(result), None, 0)
+    buf = C.create_string_buffer(max(1, n))
+    lib().vsb200_encode_frame_proto(C.byref(result), buf, n)
+    return buf.raw[:n]
