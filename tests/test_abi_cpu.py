@@ -61,3 +61,26 @@ def test_synth_is_deterministic():
     b = synth_clip(3, 80, 60, 3)
     assert np.array_equal(a, b) and a.dtype == np.uint8 and a.shape == (3, 60, 80, 3)
     assert not np.array_equal(a[0], a[1])
+
+
+def test_cpp_example_refuses_to_run_without_gpu(tmp_path):
+    """examples/over_segment_b200.cpp (the dense half of seg_tree_sample in C++ over B200DenseSegmentation + the C ABI's
+    container writer, built against the reference's headers by `make -C oracle _ref`): without an sm_100 device it
+    aborts with the C ABI's 'no CPU fallback' message instead of computing anything."""
+    import struct
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "oracle", "_ref", "over_segment_b200")
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/over_segment_b200 not built (needs /root/reference)")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    clip = np.load(os.path.join(ROOT, "tests", "golden", "real_clip_136x240x24.npz"))["frames"][:3]
+    t, h, w, _ = clip.shape
+    src = tmp_path / "in.bgr"
+    src.write_bytes(struct.pack("<iii", w, h, t) + clip.tobytes())
+    p = subprocess.run([exe, str(src), str(tmp_path / "out.pb")], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0
+    assert "no CPU fallback" in p.stderr

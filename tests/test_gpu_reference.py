@@ -78,6 +78,30 @@ def test_segmentation_file_written_from_the_engine(tmp_path, real_clip):
         assert rb.ref_io_read(path) == ([1, 0], frames, [1000 * k for k in range(len(clip))])
 
 
+def test_cpp_example_program_writes_the_reference_container(tmp_path, real_clip):
+    """examples/over_segment_b200 (C++: B200DenseSegmentation -> wire encoder -> container writer) on a B200: the file
+    it writes holds, frame for frame, the messages of the compiled reference."""
+    import os
+    import struct
+    import subprocess
+    from video_segment_b200.segio import SegmentationReader, encode_frame_proto
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "over_segment_b200")
+    if not os.path.exists(exe) or not rb.available(build=False):
+        pytest.skip("oracle/_ref/over_segment_b200 / libref_results.so not shipped")
+    clip = np.ascontiguousarray(real_clip[:12])
+    t, h, w, _ = clip.shape
+    src, dst = tmp_path / "in.bgr", tmp_path / "out.pb"
+    src.write_bytes(struct.pack("<iii", w, h, t) + clip.tobytes())
+    p = subprocess.run([exe, str(src), str(dst)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-800:]
+    r = SegmentationReader(str(dst))
+    assert r.open_file_and_read_headers() and r.num_frames() == t and r.get_header_flags() == [1, 0]
+    frames = [r.read_next_frame_binary() for _ in range(t)]
+    r.close_file()
+    ref = rc.run_stream(rb.ReferenceDense, clip, None, {})
+    assert frames == [encode_frame_proto(rb.result_struct(d)) for d in ref]
+
+
 def test_cpp_host_class_matches_compiled_reference():
     """segmentation::B200DenseSegmentation (video_segment_b200/host: the C++ class with DenseSegmentation's ProcessFrame
     signature over the C ABI, compiled against the reference's headers) on a flushed single chunk: the
