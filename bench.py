@@ -310,7 +310,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind, make, cores = cpu_engine()
-        nfr = 4
+        nfr = 8      # ~10 s of CPU work at 1080p (the reference costs ~1 s per frame; BASELINE asks for a bounded sample)
         o = make(w, h)
         t0 = time.perf_counter()
         got = 0
