@@ -25,7 +25,14 @@ inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int le
 }
 // Region-stage feature extraction (region_descriptor.cpp:59-89) is linked for its vtables only in oracle/_ref; the
 // descriptor oracle is pinned through histograms.cpp and cv2 golden vectors instead.  Abort if reached.
-inline void cvtColor(const Mat&, Mat&, int, int = 0) { std::abort(); }
+// Functional only where the including library provides vso_shim_bgr2lab (oracle/ref_hier_wrap.cpp forwards to the
+// oracle's 8-bit BGR->Lab, bit identical to cv2 4.13 over the whole colour cube); aborts elsewhere.
+extern "C" void vso_shim_bgr2lab(const unsigned char* bgr, int w, int h, int row_stride, unsigned char* lab_out) __attribute__((weak));
+inline void cvtColor(const Mat& src, Mat& dst, int code, int = 0) {
+  if (code != CV_BGR2Lab || !vso_shim_bgr2lab || src.type() != CV_8UC3) std::abort();
+  if (dst.rows != src.rows || dst.cols != src.cols || dst.type() != CV_8UC3 || !dst.data) dst.create(src.rows, src.cols, CV_8UC3);
+  for (int y = 0; y < src.rows; ++y) vso_shim_bgr2lab(src.ptr<uchar>(y), src.cols, 1, (int)src.step[0], dst.ptr<uchar>(y));
+}
 inline Scalar mean(const Mat&) { std::abort(); }
 // Not on the default path (PRESMOOTH_GAUSSIAN, compute_vectorization): third-party algorithms, abort if reached.
 inline void GaussianBlur(const Mat&, Mat&, Size, double, double = 0, int = 4) { std::abort(); }
