@@ -451,3 +451,17 @@ def test_product_host_shape_helpers_equal_reference_functions(seed):
         pytest.skip("oracle/_ref/libb200_host_check.so not built (needs /root/reference)")
     bad, msg = rb.host_shape_check(seed, 400)
     assert bad == 0, msg
+
+
+def test_oracle_equals_compiled_reference_at_1080p():
+    """BASELINE config C geometry: a flushed 3-frame 1920x1080 chunk (20 M edges) through the compiled reference and
+    the oracle (reference-style threading), identical in every field."""
+    import reference_binding as rb
+    from video_segment_b200.synth import synth
+    if not rb.available():
+        pytest.skip("oracle/_ref/libref_results.so not built (needs /root/reference)")
+    clip = np.stack(list(synth(3, 1920, 1080, 3)))
+    ref = rc.run_stream(rb.ReferenceDense, clip, None, {})
+    mine = rc.run_stream(ob.OracleDense, clip, None, dict(num_threads=os.cpu_count() or 1))
+    assert rc.first_difference(ref, mine) is None
+    assert len(ref[0]["region_id"]) > 50
