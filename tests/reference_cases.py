@@ -90,3 +90,44 @@ def first_difference(ref, mine):
                                                         y.view(np.uint32) if y.dtype.kind == "f" else y):
                 return f"frame {k} {key}: shapes {x.shape} {y.shape}"
     return None
+
+
+# ---- randomised cases (differential testing of the oracle against the compiled reference) ----
+
+def random_case(seed):
+    """A small random clip (noise / gradient + noise / moving blocks / speckles), random options inside the reference's
+    own preconditions (>= 2 overlap frames; bilateral filter needs >= 8 rows), optional random flow."""
+    rng = np.random.default_rng(seed)
+    w = int(rng.integers(9, 56)); h = int(rng.integers(8, 44)); t = int(rng.integers(1, 30))
+    kind = rng.integers(0, 4)
+    if kind == 0:      # pure noise
+        clip = rng.integers(0, 256, (t, h, w, 3), dtype=np.uint8)
+    elif kind == 1:    # low-amplitude noise over a gradient (many force-merge buckets)
+        gx = np.linspace(0, 200, w)[None, None, :, None]
+        clip = np.clip(gx + rng.normal(0, 6, (t, h, w, 3)), 0, 255).astype(np.uint8)
+    elif kind == 2:    # moving blocks
+        clip = np.zeros((t, h, w, 3), np.uint8) + rng.integers(0, 256, 3, dtype=np.uint8)
+        for k in range(t):
+            for b in range(4):
+                x0 = (b * 7 + k * (b + 1)) % max(1, w - 5); y0 = (b * 5 + k) % max(1, h - 5)
+                clip[k, y0:y0 + 5, x0:x0 + 6] = [40 * b + 30, 255 - 50 * b, 90 + 30 * b]
+        clip = np.clip(clip + rng.normal(0, 3, clip.shape), 0, 255).astype(np.uint8)
+    else:              # flat with a few speckles
+        clip = np.full((t, h, w, 3), 128, np.uint8)
+        idx = rng.integers(0, clip.size, clip.size // 50)
+        clip.reshape(-1)[idx] = rng.integers(0, 256, idx.size, dtype=np.uint8)
+    chunk = int(rng.integers(3, 13))
+    ratio = float(rng.choice([0.2, 0.3, 0.4, 0.5, 0.7]))
+    if min(int(ratio * chunk + 0.5), 2) < 2 or min(int(ratio * chunk + 0.5), 2) >= chunk:
+        chunk, ratio = 8, 0.2
+    opts = dict(chunk_size=chunk, chunk_overlap_ratio=ratio,
+                num_constraint_frames=int(rng.integers(1, 3)),
+                enforce_n4_connectivity=int(rng.integers(0, 2)), enforce_spatial_connectedness=int(rng.integers(0, 2)),
+                color_distance=int(rng.integers(0, 2)), presmoothing=int(rng.choice([0, 2])),
+                frac_min_region_size=float(rng.choice([0.01, 0.05, 0.1, 0.2])))
+    if opts["presmoothing"] == 2 and h < 8:
+        opts["presmoothing"] = 0
+    flows = None
+    if rng.integers(0, 2):
+        flows = rng.normal(0, float(rng.choice([0.5, 3.0, 20.0])), (t, h, w, 2)).astype(np.float32)
+    return np.ascontiguousarray(clip), flows, opts
