@@ -84,3 +84,23 @@ def test_cpp_example_refuses_to_run_without_gpu(tmp_path):
     p = subprocess.run([exe, str(src), str(tmp_path / "out.pb")], capture_output=True, text=True, timeout=120)
     assert p.returncode != 0
     assert "no CPU fallback" in p.stderr
+
+
+def test_reference_arm_prints_one_line_under_torchrun():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone runs the CPU reference
+    and prints ONE JSON line with the contract's keys, the other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--width", "160", "--height", "120"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-800:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["higher_is_better"] is True and line["config"]["workload"].startswith("160x120")
