@@ -170,3 +170,24 @@ def test_wire_encoder_equals_protobuf_serialisation(case, tmp_path):
         want.append(mine)
     w.write_term_header_and_close()
     assert _read(path) == ([1, 0], want, [40 * k for k in range(len(res))])
+
+
+def test_strip_and_wire_encoder_on_random_streams():
+    """The two serialisers of csrc (vsb200_strip_to_essentials, vsb200_encode_frame_proto) on the result streams of 24
+    random cases (tests/reference_cases.random_case): byte identical to the reference's StripToEssentials (where the
+    compiled reference is present) and to the protobuf runtime."""
+    from proto_schema import segmentation_desc_class
+    from video_segment_b200.segio import encode_frame_proto
+    Desc = segmentation_desc_class()
+    have_ref = rb.host_available()
+    frames = 0
+    for seed in range(24):
+        clip, flows, opts = rc.random_case(seed)
+        for d in rc.run_stream(ob.OracleDense, clip, flows, opts):
+            s = rb.result_struct(d)
+            assert encode_frame_proto(s) == _message_from_result(Desc, d).SerializeToString(deterministic=True), seed
+            if have_ref:
+                for moments in (False, True):
+                    assert strip_to_essentials(s, moments) == rb.ref_io_strip(d, moments), (seed, moments)
+            frames += 1
+    assert frames > 100
