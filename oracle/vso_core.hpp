@@ -129,6 +129,7 @@ class DenseGraph {
   Region* MergeRegions(Region* rep_1, Region* rep_2);
   float DescriptorDistance(const float* lhs, const float* rhs, float edge_distance) const;
   void SegmentGraph(int min_region_size, bool force_constraints);
+  void SimulateStage0(int64_t* stats);   // simulation of the product's force-bucket shortcut (tests only), see vso_graph.cpp
   void MergeConstrainedRegions();
   void FlattenUnionFind(bool separate_representatives);
   RegionInformation* GetCreateRegionInformation(const Region& rep, RegionInfoList* list,

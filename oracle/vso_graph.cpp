@@ -103,13 +103,94 @@ float DenseGraph::DescriptorDistance(const float* lhs, const float* rhs, float e
   return dist;
 }
 
+// ---------------------------------------------------------------------------------------------
+// NOT part of the restatement: a CPU simulation of a candidate "stage 0" shortcut for the product's merge
+// (development only, switched on with VSO_SIM_STAGE0=1 by tools/sim_stage0.py; measured at 1080p: one
+// percolating component holds 32 M of the 41 M nodes, so the shortcut was not built).  Claim under test: in the force-merge buckets (bucket * inv_scale < force_merge_weight)
+// an edge between two different un-finalised regions always merges while the two means are closer
+// than 0.2; every region mean is a convex combination of the pixel colours of its connected
+// component (edges of the force buckets), so a component whose pixel-colour box has a diagonal
+// below 0.2 and that carries at most one constraint id merges completely whatever the order.
+// Such "safe" components are merged up front (exact size-weighted mean); all the others are left
+// untouched for the ordered scan.
+// ---------------------------------------------------------------------------------------------
+void DenseGraph::SimulateStage0(int64_t* stats) {
+  const float inv_scale = 1.0 / scale_;
+  const int n = (int)regions_.size();
+  std::vector<int> cc(n);
+  std::iota(cc.begin(), cc.end(), 0);
+  auto find = [&](int x) { while (cc[x] != x) { cc[x] = cc[cc[x]]; x = cc[x]; } return x; };
+  int n_force = 0;
+  while (n_force < num_buckets_ && n_force * inv_scale < force_merge_weight_) ++n_force;
+  std::vector<char> touched(n, 0);
+  for (int b = 0; b < n_force; ++b)
+    for (auto& bl : bucket_lists_)
+      for (const auto& e : bl[b]) {
+        touched[e.region_1] = touched[e.region_2] = 1;
+        const int a = find(e.region_1), c = find(e.region_2);
+        if (a != c) cc[std::max(a, c)] = std::min(a, c);
+      }
+  struct Acc { float mn[3], mx[3]; double s[3]; int64_t sz; int con; bool multi; };
+  std::unordered_map<int, Acc> acc;
+  for (int i = 0; i < n; ++i) {
+    if (!touched[i]) continue;
+    const int r = find(i);
+    auto it = acc.find(r);
+    if (it == acc.end()) {
+      Acc a;
+      for (int k = 0; k < 3; ++k) { a.mn[k] = 1e30f; a.mx[k] = -1e30f; a.s[k] = 0; }
+      a.sz = 0; a.con = -1; a.multi = false;
+      it = acc.insert(std::make_pair(r, a)).first;
+    }
+    Acc& a = it->second;
+    const Region& R = regions_[i];
+    for (int k = 0; k < 3; ++k) {
+      a.mn[k] = std::min(a.mn[k], R.descriptor[k]);
+      a.mx[k] = std::max(a.mx[k], R.descriptor[k]);
+      a.s[k] += (double)R.descriptor[k] * R.sz;
+    }
+    a.sz += R.sz;
+    if (R.constraint_id >= 0) {
+      if (a.con >= 0 && a.con != R.constraint_id) a.multi = true;
+      a.con = std::max(a.con, R.constraint_id);
+    }
+  }
+  const float thr = 0.2f * 0.999f - 2e-5f;
+  int64_t safe_nodes = 0, unsafe_nodes = 0, unsafe_comps = 0, safe_comps = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!touched[i]) continue;
+    const int r = find(i);
+    const Acc& a = acc[r];
+    const float dx = a.mx[0] - a.mn[0], dy = a.mx[1] - a.mn[1], dz = a.mx[2] - a.mn[2];
+    const float diam = std::sqrt((dx * dx + dy * dy + dz * dz) * (1.0f / 3.0f));
+    const bool safe = !a.multi && diam < thr;
+    if (i == r) { if (safe) ++safe_comps; else ++unsafe_comps; }
+    if (!safe) { ++unsafe_nodes; continue; }
+    ++safe_nodes;
+    Region& R = regions_[i];
+    R.my_id = r;
+    if (i == r) {
+      R.sz = (int)a.sz;
+      R.constraint_id = a.con;
+      for (int k = 0; k < 3; ++k) R.descriptor[k] = (float)(a.s[k] / (double)a.sz);
+    }
+  }
+  if (stats) { stats[0] = safe_nodes; stats[1] = unsafe_nodes; stats[2] = safe_comps; stats[3] = unsafe_comps; }
+  if (getenv("VSO_SIM_STAGE0_VERBOSE"))
+    fprintf(stderr, "stage0: nodes %d safe %lld unsafe %lld comps safe %lld unsafe %lld\n", n, (long long)safe_nodes,
+            (long long)unsafe_nodes, (long long)safe_comps, (long long)unsafe_comps);
+}
+
 // segmentation_graph.h:339-463
 void DenseGraph::SegmentGraph(int min_region_size, bool force_constraints) {
+  if (getenv("VSO_SIM_STAGE0")) SimulateStage0(nullptr);
   const float inv_scale = 1.0 / scale_;
   int64_t num_forced_merges = 0, num_regular_merges = 0, num_small_region_merges = 0;
   const float merge_distance_threshold = 0.05f;   // pixel_distance.h:471
   const float split_distance_threshold = 0.15f;   // pixel_distance.h:472
   const int num_lists = (int)bucket_lists_.size();
+  const bool trace = getenv("VSO_TRACE_MERGE") != nullptr;
+  std::vector<int64_t> trace_stats(64 * 16, 0);
   for (int bucket_idx = 0; bucket_idx < num_buckets_; ++bucket_idx) {
     const float weight = bucket_idx * inv_scale;
     for (int bucket_list_idx = 0; bucket_list_idx < num_lists; ++bucket_list_idx) {
@@ -118,6 +199,28 @@ void DenseGraph::SegmentGraph(int min_region_size, bool force_constraints) {
         Region* rep_1 = GetRegion(e.region_1);
         Region* rep_2 = GetRegion(e.region_2);
         if (rep_1 == rep_2) continue;
+        if (trace) {   // development statistics only (VSO_TRACE_MERGE), no effect on the scan
+          const bool b1 = rep_1->sz >= min_region_size, b2 = rep_2->sz >= min_region_size;
+          int64_t* t = &trace_stats[(size_t)std::min(bucket_idx, 63) * 16];
+          ++t[0];
+          t[1 + (b1 ? 1 : 0) + (b2 ? 1 : 0)]++;                       // ss / sh / hh live edges
+          if (!rep_1->region_finalized && !rep_2->region_finalized && (rep_1->constraint_id < 0 || rep_2->constraint_id < 0)) {
+            const float d = DescriptorDistance(rep_1->descriptor, rep_2->descriptor, 1.0f);
+            const float thr = (weight < force_merge_weight_) ? 0.2f : 0.05f;
+            ++t[4];
+            if (d >= thr) ++t[5 + (b1 ? 1 : 0) + (b2 ? 1 : 0)];      // failed tests ss / sh / hh
+            else if (d >= 0.9f * thr) ++t[8 + (b1 ? 1 : 0) + (b2 ? 1 : 0)];   // near passes
+          }
+          if ((rep_1->region_finalized || rep_2->region_finalized) && (b1 != b2)) ++t[11];   // small into finalised/any big w/o test
+          if ((rep_1->region_finalized || rep_2->region_finalized) && b1 && b2) ++t[12];   // inert
+          if (rep_1->constraint_id >= 0 && rep_2->constraint_id >= 0) {
+            if (rep_1->constraint_id != rep_2->constraint_id) ++t[13];   // passive (different ids)
+            else {
+              ++t[14];                                                   // same-id tests
+              if (DescriptorDistance(rep_1->descriptor, rep_2->descriptor, weight) > 0.15f) ++t[15];   // splits
+            }
+          }
+        }
         if (rep_1->constraint_id < 0 || rep_2->constraint_id < 0) {
           if (!rep_1->region_finalized && !rep_2->region_finalized) {
             const float desc_distance =
@@ -162,6 +265,16 @@ void DenseGraph::SegmentGraph(int min_region_size, bool force_constraints) {
       bucket_lists_[bucket_list_idx][bucket_idx].swap(remaining_edges);
     }
   }
+  if (trace) {
+    fprintf(stderr, "bucket live ss sh hh | tests fail_ss fail_sh fail_hh near_ss near_sh near_hh | notest_abs inert | passive sameid splits\n");
+    for (int b = 0; b < 64; ++b) {
+      const int64_t* t = &trace_stats[(size_t)b * 16];
+      if (!t[0]) continue;
+      fprintf(stderr, "%2d %9lld %9lld %9lld %7lld | %9lld %6lld %6lld %6lld %6lld %6lld %6lld | %8lld %8lld | %8lld %8lld %6lld\n", b, (long long)t[0], (long long)t[1],
+              (long long)t[2], (long long)t[3], (long long)t[4], (long long)t[5], (long long)t[6], (long long)t[7], (long long)t[8],
+              (long long)t[9], (long long)t[10], (long long)t[11], (long long)t[12], (long long)t[13], (long long)t[14], (long long)t[15]);
+    }
+  }
   if (force_constraints) MergeConstrainedRegions();
   merge_stats[0] = num_regular_merges;
   merge_stats[1] = num_small_region_merges;
@@ -176,9 +289,20 @@ void DenseGraph::MergeConstrainedRegions() {
   virtual_nodes.push_back(std::make_pair((int)regions_.size(), (int)regions_.size()));
   std::sort(virtual_nodes.begin(), virtual_nodes.end());
   const float split_distance_threshold = 0.15f;
+  // development switch (not part of the restatement): VSO_SIM_MCR=1 visits every representative once, at its first
+  // node, plus one immediate re-visit when it loses its constraint -- the product's round-1 walk, kept to measure
+  // what that shortcut costs against the real loop below.
+  const bool sim_first_only = getenv("VSO_SIM_MCR") != nullptr;
+  std::vector<char> seen_rep(sim_first_only ? regions_.size() : 0, 0);
   for (size_t k = 1; k < virtual_nodes.size(); ++k) {
     for (int idx = virtual_nodes[k - 1].second, end_idx = virtual_nodes[k].first; idx < end_idx; ++idx) {
       if (regions_[idx].constraint_id < 0) continue;
+      if (sim_first_only) {
+        Region* r = GetRegion(regions_[idx].my_id);
+        if (seen_rep[r->my_id] >= 1) { if (!(seen_rep[r->my_id] == 2)) continue; seen_rep[r->my_id] = 1; }
+        else seen_rep[r->my_id] = 1;
+        if (idx >= 2 * w_ * h_) continue;     // slot 1 only
+      }
       Region* my_rep = GetRegion(regions_[idx].my_id);
       auto pos = constraint_to_region_map.find(my_rep->constraint_id);
       if (pos == constraint_to_region_map.end()) {
@@ -188,6 +312,7 @@ void DenseGraph::MergeConstrainedRegions() {
         if (constraint_rep != my_rep) {
           const float distance = DescriptorDistance(my_rep->descriptor, constraint_rep->descriptor, 1.0f);
           if (distance > split_distance_threshold) {
+            const int before = my_rep->constraint_id;
             if (my_rep->sz < constraint_rep->sz * 0.3) {
               my_rep->constraint_id = -1;
             } else if (constraint_rep->sz < my_rep->sz * 0.3) {
@@ -198,8 +323,10 @@ void DenseGraph::MergeConstrainedRegions() {
               constraint_rep->constraint_id = -1;
               constraint_to_region_map.erase(pos);
             }
+            if (sim_first_only && before >= 0 && my_rep->constraint_id < 0) seen_rep[my_rep->my_id] = 2;
           } else {
-            MergeRegions(my_rep, constraint_rep);
+            Region* m = MergeRegions(my_rep, constraint_rep);
+            if (sim_first_only) seen_rep[m->my_id] = 1;
           }
         }
       }
