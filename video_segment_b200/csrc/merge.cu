@@ -279,6 +279,7 @@ constexpr int kScHubs3 = 4;      // sub-cluster touches more than two hubs
 constexpr int kScUnc = 8;        // hub: may meet another un-finalised hub through a shared sub-cluster
 constexpr int kScCertYes = 32;     // cached verdict of subcluster_certified for this segment attempt
 constexpr int kScCertNo = 64;
+constexpr int kScSplitCap = 128;   // constrained chunks: an uncertified same-id edge touches this hub / sub-cluster (its id may be reset in the segment)
 constexpr int kScUncAny = 16;    // hub: may meet a hub with the same constraint id through a shared sub-cluster (flags do not matter)
 #ifndef VSB_WINDOW_TARGET
 #define VSB_WINDOW_TARGET (1ull << 18)
@@ -451,6 +452,7 @@ struct ScanShared {
 struct MergeShared {
   ScanShared scan;
   unsigned warp_cnt[kMergeWarps];
+  unsigned warp_live[kMergeWarps];
 };
 
 // block-wide exclusive scan of a 0/1 flag; returns the rank of the calling thread, total via *total
@@ -642,7 +644,8 @@ __device__ int ordered_rounds(const MergeParams& p, Bar& bar, const unsigned tid
       if (!drop) {
         const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
         const bool both_con = (A.con >= 0 && B.con >= 0);
-        drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+        // (edges between different constraint ids are only here as guards: they wait for their turn like any other edge)
+        drop = (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
         bigbig = !drop && A.sz >= mins && B.sz >= mins;
       }
       if (drop) { p.done[pos] = 1; continue; }
@@ -742,6 +745,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
   unsigned long long w0 = 0;
   unsigned long long target = kWindowTarget;   // live edges aimed at per window: grows while windows certify cleanly
   unsigned long long raw = min(bucket_edges, kWindowTarget);
+  const bool tiny_windows = p.has_constraints && (p.dev_flags & 64);      // diagnostic: prune state (nearly) exact
+  const bool no_cert = p.has_constraints && (p.dev_flags & 32);           // diagnostic: every edge through rounds + exact scans
+  if (tiny_windows) { target = 4096; raw = min(bucket_edges, 4096ull); }
   unsigned long long guard = 0;
   uint32_t* const master = p.live_a;            // live list of the window (code, ru, rv, position)
   unsigned long long t_phase = 0, t_cpass = 0;
@@ -763,11 +769,11 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
     uint32_t* const hub_mask = p.live_b + (n_edges >> 5) + 1;
     unsigned long long* const warp_cnt = p.counters + 16;
     {
-      unsigned my_count = 0;
+      unsigned my_count = 0, my_live = 0;
       for (unsigned long long base = c0; base < c1; base += 32ull * kP1U) {
         uint32_t code[kP1U];
         int us[kP1U], vs[kP1U], pu[kP1U], pv[kP1U], rus[kP1U], rvs[kP1U];
-        bool in[kP1U], keep[kP1U], hubf[kP1U];
+        bool in[kP1U], keep[kP1U], hubf[kP1U], livef[kP1U];
 #pragma unroll
         for (int k = 0; k < kP1U; ++k) {
           const unsigned long long i = base + 32ull * k + lane;
@@ -801,20 +807,24 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
         }
 #pragma unroll
         for (int k = 0; k < kP1U; ++k) {
-          keep[k] = false; hubf[k] = false;
+          keep[k] = false; hubf[k] = false; livef[k] = false;
           if (!in[k]) continue;
           const unsigned long long i = base + 32ull * k + lane;
           bool drop = (rus[k] == rvs[k]);
+          bool dormant = false;
           if (!drop) {
             const int asz = a0[k].x, acon = a0[k].y, bsz = b0[k].x, bcon = b0[k].y;
             const bool both_con = (acon >= 0 && bcon >= 0);
-            drop = (both_con && acon != bcon)
-                   || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
+            // different constraint ids: nothing happens NOW, but a split may reset one of the ids before the scan
+            // reaches the edge (segmentation_graph.h:417-437), so the entry stays in the list as dormant (done = 3)
+            dormant = both_con && acon != bcon;
+            drop = dormant || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
             hubf[k] = !drop && asz >= mins && bsz >= mins;
           }
-          p.done[i] = drop ? 1 : 0;                // done flags of the window are (re)written here
-          keep[k] = !drop;
-          if (!drop) staging[i] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
+          p.done[i] = dormant ? 3 : (drop ? 1 : 0);   // done flags of the window are (re)written here
+          keep[k] = !drop || dormant;
+          livef[k] = !drop;
+          if (keep[k]) staging[i] = make_uint4(code[k], (uint32_t)rus[k], (uint32_t)rvs[k], (uint32_t)i);
         }
 #pragma unroll
         for (int k = 0; k < kP1U; ++k) {           // warp-uniform: chunk bounds are multiples of 32
@@ -823,25 +833,29 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
           const unsigned m2 = __ballot_sync(0xffffffffu, hubf[k]);
           if (lane == 0 && g0 < c1) { keep_mask[g0 >> 5] = m; hub_mask[g0 >> 5] = m2; }
           my_count += __popc(m);
+          my_live += __popc(__ballot_sync(0xffffffffu, livef[k]));
         }
       }
       // two-level counts: warps of a block in shared memory, blocks in global memory
       const unsigned wib = threadIdx.x >> 5;
-      if (lane == 0) S.warp_cnt[wib] = my_count;
+      if (lane == 0) { S.warp_cnt[wib] = my_count; S.warp_live[wib] = my_live; }
       __syncthreads();
       if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int k = 0; k < kMergeWarps; ++k) t += S.warp_cnt[k];
+        unsigned long long t = 0, tl = 0;
+        for (int k = 0; k < kMergeWarps; ++k) { t += S.warp_cnt[k]; tl += S.warp_live[k]; }
         warp_cnt[kIsGrid ? blockIdx.x : 0u] = t;
+        warp_cnt[1024 + (kIsGrid ? blockIdx.x : 0u)] = tl;
       }
     }
     bar.sync();
-    unsigned long long n_master = 0;
+    unsigned long long n_master = 0, n_live0 = 0;
     {
       const unsigned nblk = kIsGrid ? gridDim.x : 1u, blk = kIsGrid ? blockIdx.x : 0u, wib = threadIdx.x >> 5;
       unsigned long long before = 0, total = 0;
-      for (unsigned j = lane; j < nblk; j += 32) { const unsigned long long c = *((volatile unsigned long long*)&warp_cnt[j]); total += c; if (j < blk) before += c; }
-      for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); }
+      unsigned long long total_live = 0;
+      for (unsigned j = lane; j < nblk; j += 32) { const unsigned long long c = *((volatile unsigned long long*)&warp_cnt[j]); total += c; if (j < blk) before += c; total_live += *((volatile unsigned long long*)&warp_cnt[1024 + j]); }
+      for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); total += __shfl_xor_sync(0xffffffffu, total, o); total_live += __shfl_xor_sync(0xffffffffu, total_live, o); }
+      n_live0 = total_live;
       for (unsigned k = 0; k < wib; ++k) before += S.warp_cnt[k];
       n_master = total;
       unsigned long long off = before;
@@ -1044,7 +1058,8 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
             if (!VSB_IN_SEG(e)) continue;
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;
             bool cert = false;
-            if (sa < mins || sb < mins) {
+            if (no_cert) {
+            } else if (sa < mins || sb < mins) {
               const int c = cl_find_compress(p.cl, sa < mins ? (int)e.y : (int)e.z);
               // the verdict is a function of the sub-cluster: the first edges to ask compute it, the rest read it
               const int fl = *((volatile int*)&p.hull[c].flags);
@@ -1058,6 +1073,22 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
               if (!cert && p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8 + subcluster_why(p, load_sc(&p.hull[c]), wt, mins)], 1ull);
             } else if (p.debug) atomicAdd(&p.debug[kNumBuckets * 4 + 8], 1ull);
             if (!cert) ++mine;
+            if (!cert && p.has_constraints) {
+              // an uncertified same-id edge may reset a constraint id (split); dormant edges of whatever it touches
+              // become guards of this segment (C5)
+              const int ca = p.rec[e.y].con, cb = p.rec[e.z].con;
+              if (ca >= 0 && ca == cb) {
+                // the split resets the id of the side smaller than 0.3 x the other one (both if neither is): a hub
+                // keeps its id whenever the whole sub-cluster on the other side weighs less than 0.3 x the hub
+                NodeScratch* ta = &p.hull[sa >= mins ? (int)e.y : cl_find_compress(p.cl, (int)e.y)];
+                NodeScratch* tb = &p.hull[sb >= mins ? (int)e.z : cl_find_compress(p.cl, (int)e.z)];
+                bool ma = true, mb = true;
+                if (sa >= mins && sb < mins) ma = !((double)tb->mass < (double)sa * 0.29);
+                if (sb >= mins && sa < mins) mb = !((double)ta->mass < (double)sb * 0.29);
+                if (ma && !(*((volatile int*)&ta->flags) & kScSplitCap)) atomicOr(&ta->flags, kScSplitCap);
+                if (mb && !(*((volatile int*)&tb->flags) & kScSplitCap)) atomicOr(&tb->flags, kScSplitCap);
+              }
+            }
           }
           for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
           if (lane == 0 && mine) atomicAdd(&p.counters[5], mine);
@@ -1070,12 +1101,33 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
         if (!split) {
           for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
             const uint4 e = reinterpret_cast<const uint4*>(master)[i];
-            if (!VSB_IN_SEG(e)) continue;
+            const unsigned char dn0 = p.done[e.w];
+            if (dn0 == 3) {
+              // dormant edge (different constraint ids): a guard of this segment if a split may reach one of its
+              // sides -- then the exact paths decide it in order; otherwise it is a certified no-op
+              bool guard = false;
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) {
+                const int r = s2 ? (int)e.z : (int)e.y;
+                if (p.rec[r].sz >= mins) guard = guard || (p.hull[r].flags & kScSplitCap);
+                else {
+                  const NodeScratch SCg = load_sc(&p.hull[cl_find_compress(p.cl, r)]);
+                  guard = guard || (SCg.flags & kScSplitCap);
+                  if (SCg.hub0 >= 0) guard = guard || (p.hull[SCg.hub0].flags & kScSplitCap);
+                  if (SCg.hub1 >= 0) guard = guard || (p.hull[SCg.hub1].flags & kScSplitCap);
+                  if (SCg.flags & kScHubs3) guard = true;
+                }
+              }
+              p.done[e.w] = guard ? 0 : 1;
+              continue;
+            }
+            if (dn0) continue;
             const int sa = p.rec[e.y].sz, sb = p.rec[e.z].sz;    // sizes are not folded before the next barrier
             if (sa >= mins && sb >= mins) continue;
             const int c = cl_find_compress(p.cl, sa < mins ? (int)e.y : (int)e.z);
             const NodeScratch SC = load_sc(&p.hull[c]);
             const int target = (SC.hub0 >= 0) ? SC.hub0 : c;        // certified sub-clusters touch at most one hub
+            if (no_cert) continue;
             if (!(SC.flags & kScCertYes)) {
               // the ordered rounds may let frozen hubs absorb: publish the certificate
 #pragma unroll
@@ -1106,7 +1158,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
         for (unsigned long long i = seg_lo + tid; i < seg_hi; i += nthr) {
           const uint4 e = reinterpret_cast<const uint4*>(master)[i];
           const unsigned char dn = p.done[e.w];
-          if (dn == 1) continue;                  // was not part of this attempt
+          if (dn == 1 || dn == 3) continue;       // was not part of this attempt / still dormant (the segment is being halved)
 #pragma unroll
           for (int s2 = 0; s2 < 2; ++s2) {
             const int r = s2 ? (int)e.z : (int)e.y;
@@ -1293,17 +1345,25 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
       bar.sync();
       for (unsigned long long i = seg_lo + tid; i < n_master; i += nthr) {
         uint4 e = reinterpret_cast<const uint4*>(master)[i];
-        if (p.done[e.w]) continue;
+        const unsigned char dn = p.done[e.w];
+        if (dn == 1) continue;
         const int ru = uf_find(p.parent, (int)e.y), rv = uf_find(p.parent, (int)e.z);
         bool drop = (ru == rv);
-        bool hubhub = false;
+        bool hubhub = false, dormant = false;
         if (!drop) {
           const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
           const bool both_con = (A.con >= 0 && B.con >= 0);
-          drop = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
-          hubhub = !drop && A.sz >= mins && B.sz >= mins;
+          dormant = both_con && A.con != B.con;
+          drop = (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+          hubhub = !drop && !dormant && A.sz >= mins && B.sz >= mins;
         }
         if (drop) { p.done[e.w] = 1; continue; }
+        if (dormant) {
+          if (dn != 3) p.done[e.w] = 3;
+          if (ru != (int)e.y || rv != (int)e.z) { e.y = (uint32_t)ru; e.z = (uint32_t)rv; reinterpret_cast<uint4*>(master)[i] = e; }
+          continue;
+        }
+        if (dn == 3) p.done[e.w] = 0;          // a dormant edge woke up (one side lost its constraint id)
         if (hubhub) atomicMin(&p.counters[4], i);
         if (ru != (int)e.y || rv != (int)e.z) { e.y = (uint32_t)ru; e.z = (uint32_t)rv; reinterpret_cast<uint4*>(master)[i] = e; }
       }
@@ -1315,13 +1375,14 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
     w0 += n_edges;
     {
       if (any_split) target = max(target / 2, kWindowTarget / 4);
-      else if (unc_sum * 64 <= n_master && !(p.dev_flags & 2)) target = min(target * 2, kWindowTarget * 32);
-      const unsigned long long live0 = n_master ? n_master : 1;
+      else if (unc_sum * 64 <= n_live0 && !(p.dev_flags & 2)) target = min(target * 2, kWindowTarget * 32);
+      const unsigned long long live0 = n_live0 ? n_live0 : 1;
       unsigned long long next = raw;
       if (live0 * 2 < target) next = raw * 2;
       if (live0 * 8 < target) next = raw * 4;
       if (live0 > target * 2) next = raw / 2;
       raw = max(next, kWindowMin);
+      if (tiny_windows) { raw = 4096; target = 4096; }
     }
     ++epoch;
     bar.sync();
