@@ -30,6 +30,7 @@ extern "C" {
 #define VSB200_ERR_CUDA 3         /* CUDA runtime error (message via vsb200_last_error) */
 #define VSB200_ERR_EMPTY 4        /* pop with nothing ready */
 #define VSB200_ERR_UNSUPPORTED 5  /* option the reference has but this path does not build */
+#define VSB200_ERR_CAPACITY 6     /* a result table would outgrow its hard limit (message names it) */
 
 /* Mirrors DenseSegmentationOptions (segmentation/dense_segmentation.h:42-95) plus the
  * gflags that override it (segmentation/dense_segmentation.cpp:39-46,55-101). */
@@ -220,6 +221,9 @@ const int64_t* vsb200_seg_reader_time_stamps(const vsb200_seg_reader*);
 /* SeekToFrame + ReadNextFrameBinary (:253-274): returns the payload size of `frame`, copying min(size, cap) bytes;
  * 0 on a parse error. */
 size_t vsb200_seg_reader_read(vsb200_seg_reader*, int frame, uint8_t* buf, size_t cap);
+/* Same with a status: VSB200_OK and *size_out = payload size (0 is a legitimately empty frame), VSB200_ERR_INVALID on a
+ * parse error / truncated file. */
+int vsb200_seg_reader_read_frame(vsb200_seg_reader*, int frame, uint8_t* buf, size_t cap, size_t* size_out);
 void vsb200_seg_reader_close(vsb200_seg_reader*);
 
 /* StripToEssentials(desc, save_vectorization = false, save_shape_moments, &binary) (segmentation_io.cpp:311-443) from

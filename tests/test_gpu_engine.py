@@ -121,6 +121,64 @@ def test_1080p_chunk_matches_oracle():
         assert abs(len(g["region_id"]) - len(r["region_id"])) <= max(2, len(r["region_id"]) // 100)
 
 
+def _chunk_trajectory(frames):
+    """(chunk id, regions in the chunk's first frame) per chunk, in stream order."""
+    out, seen = [], set()
+    for f in frames:
+        if f["chunk_id"] not in seen:
+            seen.add(f["chunk_id"])
+            out.append((f["chunk_id"], len(f["region_id"])))
+    return out
+
+
+def test_1080p_constrained_chunks_match_oracle():
+    """The benched workload (BASELINE config C): 1080p, three chunks -- one free, two constrained by the
+    chunk before -- against the oracle, every frame.  Bar: IoU >= 0.99 on every frame; region counts within
+    max(3, 5 %) per frame; the free chunk partition-exact."""
+    clip = synth_clip(2, 1920, 1080, 41)
+    got, batches, st = _run_gpu(clip)
+    ref = _run_oracle(clip)
+    ious = _compare(got, ref, exact=False)
+    same = [bool(partition_equal(ob.id_map_from_result(r), g["id_map"])) for g, r in zip(got, ref)]
+    print("1080p x 41: min IoU", min(ious), "exact frames", sum(same), "regions gpu/ref per chunk",
+          _chunk_trajectory(got), _chunk_trajectory(ref))
+    assert all(same[:19])
+    assert [b for b in batches if b] == [19, 19, 3]
+    for g, r in zip(got, ref):
+        nr = len(r["region_id"])
+        assert abs(len(g["region_id"]) - nr) <= max(3, nr // 20), (len(g["region_id"]), nr)
+
+
+def test_config_b_300_frames_tracks_oracle():
+    """BASELINE config B for real: 640x480 x 300 synthetic frames = 16 chunks, every frame against the oracle.
+    Settles whether the region count grows chunk over chunk in the product only (profiles/r01_merge_constant_sweeps):
+    the per-chunk trajectory of the product must track the oracle's."""
+    clip = synth_clip(7, 640, 480, 300)
+    got, batches, st = _run_gpu(clip)
+    ref = _run_oracle(clip)
+    ious = _compare(got, ref, exact=False)
+    tg, tr = _chunk_trajectory(got), _chunk_trajectory(ref)
+    print("config B: min IoU", min(ious), "mean", float(np.mean(ious)), "trajectory gpu", tg, "ref", tr)
+    assert len(tg) == len(tr) == 16
+    for (cg, ng), (cr, nr) in zip(tg, tr):
+        assert cg == cr and abs(ng - nr) <= max(3, nr // 20), (cg, ng, nr)
+
+
+def test_1080p_flow_chunks_match_oracle():
+    """The reference's default mode (seg_tree_sample --flow): flow-displaced temporal edges at 1080p, one free and
+    one constrained chunk."""
+    pairs = list(synth_flow(4, 1920, 1080, 24))
+    clip = [p[0] for p in pairs]
+    flows = [p[1] for p in pairs]
+    got, batches, st = _run_gpu(clip, flows)
+    ref = _run_oracle(clip, flows)
+    ious = _compare(got, ref, exact=False)
+    print("1080p flow: min IoU", min(ious))
+    for g, r in zip(got, ref):
+        nr = len(r["region_id"])
+        assert abs(len(g["region_id"]) - nr) <= max(3, nr // 20), (len(g["region_id"]), nr)
+
+
 def test_flow_path_matches_oracle():
     pairs = list(synth_flow(21, 160, 120, 24))
     clip = [p[0] for p in pairs]
@@ -287,4 +345,6 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         u4.process_frame(np.zeros((10, 10, 3), np.uint8))
     assert u4.post_process() == []                                     # flush with nothing buffered
+    with pytest.raises(RuntimeError):                                  # a flushed handle is finished
+        u4.process_frame(np.zeros((48, 64, 3), np.uint8))
     u4.close()

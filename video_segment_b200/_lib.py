@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     "vsb200_region_hist_finish", "vsb200_hist_chisquare",
     "vsb200_seg_writer_open", "vsb200_seg_writer_add", "vsb200_seg_writer_add_last_frame", "vsb200_seg_writer_write_chunk",
     "vsb200_seg_writer_close", "vsb200_seg_reader_open", "vsb200_seg_reader_num_frames", "vsb200_seg_reader_num_header_flags",
-    "vsb200_seg_reader_header_flags", "vsb200_seg_reader_time_stamps", "vsb200_seg_reader_read", "vsb200_seg_reader_close",
+    "vsb200_seg_reader_header_flags", "vsb200_seg_reader_time_stamps", "vsb200_seg_reader_read", "vsb200_seg_reader_read_frame", "vsb200_seg_reader_close",
     "vsb200_strip_to_essentials", "vsb200_encode_frame_proto",
 ]
 
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         "vsb200_seg_reader_header_flags": ([vp], C.POINTER(C.c_int32)),
         "vsb200_seg_reader_time_stamps": ([vp], C.POINTER(C.c_int64)),
         "vsb200_seg_reader_read": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
+        "vsb200_seg_reader_read_frame": ([vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)], C.c_int),
         "vsb200_seg_reader_close": ([vp], None),
         "vsb200_strip_to_essentials": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
         "vsb200_encode_frame_proto": ([vp, vp, C.c_size_t], C.c_size_t),

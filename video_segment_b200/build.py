@@ -17,6 +17,9 @@ SOURCES = ["preprocess.cu", "edges.cu", "sort.cu", "merge.cu", "results.cu", "re
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    # host-side float code (constraint walk, shape moments, tube areas) must round like the reference's scalar code on
+    # every host ISA: no a*b+c contraction (GCC's default is -ffp-contract=fast where the target has FMA)
+    "-Xcompiler", "-ffp-contract=off",
 ]
 
 

@@ -86,7 +86,8 @@ struct MergeParams {
   int min_region_size;
   float force_merge_weight;        // 0.001f (L2) / 0.002f (L1), dense_segmentation.cpp:259-264
   int has_constraints;             // chunk > 0
-  int dev_flags;                   // development switches (VSB200_MERGE_FLAGS): 1 = no hub-pair certificates, 2 = fixed window target, 4 = no block-0 rounds, 16 = no group-parallel scans; default 17
+  float y_merge, y_force;          // squared-distance images of the merge gates: sqrtf(y) < 0.05f <=> y < y_merge, (double)sqrtf(y) < 0.2 <=> y < y_force (set by launch_merge)
+  int dev_flags;                   // development switches (VSB200_MERGE_FLAGS): 1 = no hub-pair certificates, 2 = fixed window target, 4 = no block-0 rounds, 16 = no group-parallel scans, 32 / 64 = diagnostics for constrained chunks, 128 = one-thread exact scans; default 17
   const float* flows;              // optional [slots][h][w][2] (slot 0 unused), nullable
   const uint32_t* codes;           // sorted edge codes
   const unsigned long long* bucket_start;   // [2049]

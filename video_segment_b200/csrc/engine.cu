@@ -59,6 +59,7 @@ struct vsb200_dense {
   // DenseSegmentation members (dense_segmentation.h:198-230)
   int input_frames = 0, chunk_id = 0, overlap_frames = 2, constraint_frames = 1;
   int max_region_id = 0, num_output_frames = 0, curr_chunk_start = 0;
+  bool flushed = false;            // PostProcess ran: the chain is finished, further pushes are refused
   bool import_pending = false;     // import_halo done, the group's first frame (slot 1) not pushed yet
   int buffered = 0;              // == feature_buffer_.size(): graph slots in use
   int max_slots = 0;
@@ -211,8 +212,8 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
   if (!bgr || stride < w * 3) { set_error("push: bad frame buffer"); return VSB200_ERR_INVALID; }
   if (use_flow && (input_frames > 0 || import_pending) && !flow) { set_error("push: flow missing (created with use_flow)"); return VSB200_ERR_INVALID; }
   if (buffered >= max_slots) { set_error("push: internal slot overflow"); return VSB200_ERR_INVALID; }
+  if (flushed) { set_error("push after flush: a flushed handle is finished (create a new one for the next sequence)"); return VSB200_ERR_INVALID; }
   ENG_CUDA(cudaSetDevice(o.device));
-  pts_queue.push_back(pts);
   const double t0 = now_ms();
   const int slot = buffered;
   if (device_input) {
@@ -250,6 +251,7 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
   }
   ENG_CUDA(cudaStreamSynchronize(stream));            // h_bgr is reused by the next push
   stats[0] += now_ms() - t0;
+  pts_queue.push_back(pts);            // after the last step that can fail: pts and results stay in step
   ++buffered;
   ++input_frames;
   if (buffered - curr_chunk_start >= o.chunk_size) return chunk_boundary(false, n_ready);
@@ -258,9 +260,11 @@ int vsb200_dense::push(const uint8_t* bgr, int stride, const float* flow, int fl
 
 int vsb200_dense::flush(int* n_ready) {
   if (n_ready) *n_ready = 0;
-  if (buffered == 0) return 0;
+  if (buffered == 0) { flushed = true; return 0; }
   ENG_CUDA(cudaSetDevice(o.device));
-  return chunk_boundary(true, n_ready);
+  const int rc = chunk_boundary(true, n_ready);
+  if (rc == 0) flushed = true;
+  return rc;
 }
 
 // Renders the region-id image of a result (SegmentationDescToIdImage, segmentation_util.cpp:741-770)
@@ -462,8 +466,12 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     for (auto& ev2 : edge_events) { float ms = 0; cudaEventElapsedTime(&ms, ev2.first, ev2.second); edge_ms += ms; edge_launches += 1; cudaEventDestroy(ev2.first); cudaEventDestroy(ev2.second); }
     edge_events.clear();
   }
-  cudaEvent_t ev[5];
-  for (auto& e : ev) cudaEventCreate(&e);
+  struct EventSet {          // destroyed on every exit path
+    cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    EventSet() { for (auto& x : e) cudaEventCreate(&x); }
+    ~EventSet() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    cudaEvent_t& operator[](int i) { return e[i]; }
+  } ev;
   // ---------------- sort ----------------
   const int num_lists = 2 * slots - 1;
   std::vector<const float*> seg(num_lists, nullptr);
@@ -526,6 +534,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
       fprintf(f, "certify passes ms: C1 union %.1f C2 records %.1f C3 hubs %.1f C4 count %.1f C5 apply %.1f C6 fold+reset %.1f\n",
               c[32] / 1e6, c[33] / 1e6, c[34] / 1e6, c[35] / 1e6, c[36] / 1e6, c[37] / 1e6);
       fprintf(f, "hub_not_frozen reasons: same_id_or_hubs3 %llu con_conflict %llu open_hubs3 %llu bound %llu\n", c[8], c[9], c[10], c[11]);
+      fprintf(f, "scans: event thread Mcycles %.1f, total %.1f (staging+sort %.1f, sub-cluster replay %.1f); staged roots %llu, events %llu of %llu edges\n", c[42] / 1e6, c[43] / 1e6, c[45] / 1e6, c[46] / 1e6, c[44], c[47], c[48]);
       fclose(f);
     }
   }
@@ -671,16 +680,29 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     ENG_CUDA(cudaMemcpyAsync(d_runs, relabel.data(), sizeof(RunRec) * relabel.size(), cudaMemcpyHostToDevice, stream));
     ENG_RC(launch_relabel(d_runs, (int)relabel.size(), w, h, d_labels, stream));
   }
-  ENG_RC(launch_neighbor_pairs(d_roots, d_labels, w, h, slots, use_flow ? d_flows : nullptr, constrained_chunk ? 1 : 0,
-                               d_pair_table, pair_table_cap, d_pairs, d_pair_count, pairs_cap, stream));
   unsigned long long n_pairs = 0;
-  ENG_CUDA(cudaMemcpyAsync(&n_pairs, d_pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));
-  cudaEventRecord(ev[4], stream);
-  ENG_CUDA(cudaStreamSynchronize(stream));
-  if (n_pairs > pairs_cap || n_pairs * 2 > pair_table_cap) {
-    set_error("neighbour pair table overflow (%llu pairs)", n_pairs);
-    return VSB200_ERR_CUDA;
+  for (int attempt = 0;; ++attempt) {
+    ENG_RC(launch_neighbor_pairs(d_roots, d_labels, w, h, slots, use_flow ? d_flows : nullptr, constrained_chunk ? 1 : 0,
+                                 d_pair_table, pair_table_cap, d_pairs, d_pair_count, pairs_cap, stream));
+    ENG_CUDA(cudaMemcpyAsync(&n_pairs, d_pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));
+    ENG_CUDA(cudaStreamSynchronize(stream));
+    if (n_pairs <= pairs_cap && n_pairs * 2 <= pair_table_cap) break;
+    // more distinct neighbour pairs than the tables hold (small min region size, large frames): the count is exact
+    // as long as the hash table itself did not fill up, so size both for it (with head room) and run the pass again
+    if (attempt >= 4 || pair_table_cap >= (1u << 30)) {
+      set_error("neighbour pair tables cannot hold %llu pairs", n_pairs);
+      return VSB200_ERR_CAPACITY;
+    }
+    unsigned long long want = std::max<unsigned long long>(n_pairs * 2, pairs_cap * 4);
+    unsigned cap = 1u << 22;
+    while ((unsigned long long)cap < want * 2 && cap < (1u << 30)) cap <<= 1;
+    cudaFree(d_pair_table); cudaFree(d_pairs);
+    d_pair_table = nullptr; d_pairs = nullptr;
+    pair_table_cap = cap; pairs_cap = cap / 2;
+    ENG_CUDA(cudaMalloc(&d_pair_table, sizeof(unsigned long long) * pair_table_cap));
+    ENG_CUDA(cudaMalloc(&d_pairs, sizeof(unsigned long long) * pairs_cap));
   }
+  cudaEventRecord(ev[4], stream);
   std::vector<unsigned long long> pairs(n_pairs);
   if (n_pairs) ENG_CUDA(cudaMemcpy(pairs.data(), d_pairs, sizeof(unsigned long long) * n_pairs, cudaMemcpyDeviceToHost));
   d2h_bytes += 8.0 * n_pairs + 8.0 * regions.size();
@@ -823,7 +845,6 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   cudaEventElapsedTime(&ms, ev[1], ev[2]); stats[3] += ms;
   cudaEventElapsedTime(&ms, ev[2], ev[3]); stats[4] += ms;
   cudaEventElapsedTime(&ms, ev[3], ev[4]); stats[6] += ms;
-  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 

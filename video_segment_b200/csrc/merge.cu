@@ -22,7 +22,9 @@
 // One persistent cooperative launch walks all 2048 buckets; buckets with few pending edges
 // are finished by block 0 alone behind __syncthreads instead of grid-wide barriers.
 #include <cooperative_groups.h>
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -509,6 +511,8 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
   const float edge_w = (float)b * (float)(1.0 / (double)bucket_scale());
   const int mins = p.min_region_size;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  long long t_scan0 = 0, t_walk0 = 0, t_walk1 = 0;
+  if (p.debug && tid == 0) t_scan0 = clock64();
   unsigned char* const ishub = reinterpret_cast<unsigned char*>(C.tru);     // tru / trv are free once the ids are looked up
   unsigned char* const skip = reinterpret_cast<unsigned char*>(C.trv);      // per edge: left pending (deferred group)
   int hbits = 6;
@@ -541,6 +545,7 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
   for (int i = tid; i < n_pend; i += nthr) skip[i] = 0;
   __syncthreads();
   if (tid == 0) {
+    if (p.debug) t_walk0 = clock64();
     auto findl = [&](int x) { int q = C.par[x]; while (q != x) { const int g = C.par[q]; C.par[x] = (unsigned short)g; x = q; q = g; } return x; };
     uint32_t deferred[16];
     int n_def = 0;
@@ -592,6 +597,7 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
       if (r == 1) C.par[bq] = (unsigned short)a;
       else if (r == 2) C.par[a] = (unsigned short)bq;
     }
+    if (p.debug) t_walk1 = clock64();
   }
   __syncthreads();
   for (int j = tid; j < n_roots; j += nthr) {
@@ -607,6 +613,250 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
   for (int i = tid; i < n_pend; i += nthr) if (!skip[i]) done_flags[C.epos[i]] = 1;
   if (tid == 0) atomicAdd(&p.stats[3], 1ull);
   __syncthreads();
+  if (p.debug && tid == 0) {      // development tap: cycles of the one-thread walk / of the whole scan (staging + walk + write-back)
+    atomicAdd(&p.debug[kNumBuckets * 4 + 50], (unsigned long long)(t_walk1 - t_walk0));
+    atomicAdd(&p.debug[kNumBuckets * 4 + 51], (unsigned long long)(clock64() - t_scan0));
+    atomicAdd(&p.debug[kNumBuckets * 4 + 52], (unsigned long long)n_roots);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split scan: the exact scan of one ordered list (<= kScanMax pending edges, every root owned by this
+// CTA) without the one-thread walk over every edge (measured: 683 cycles per edge, 97 % of the scan).
+// The walk is split along what actually depends on what:
+//   * a region below min_region_size always merges with whatever a live edge joins it to
+//     (segmentation_graph.h:375-440: regular merge, or small-region merge after a failed test), and
+//     the bigger side survives.  So the evolution of the SMALL regions -- who merges with whom, which
+//     piece reaches which big region ("hub") at which edge, the pieces' own means and flags -- does
+//     not depend on the hubs' records at all.  Small regions joined by small-small edges form
+//     sub-clusters; ONE THREAD PER SUB-CLUSTER replays its edges in order with the exact decision
+//     tree and logs, per edge, what it does to a hub: ABSORB (hub, piece) or BB (two hubs meet: a
+//     static big-big edge, or two pieces of the sub-cluster sitting in different hubs).  A piece
+//     that grows to min_region_size is a hub from that edge on (its record is final for the thread).
+//   * the hubs' records -- means, flags, constraint ids, big-big merges -- evolve along the logged
+//     events only: one thread replays the events in reference order (absorb: ~100 cycles with the
+//     hub's record in registers and the gates taken on the squared distance; big-big: the generic
+//     decision tree).
+//   * the one conditional case, a constrained piece meeting a hub (same id: merge only within 0.15;
+//     other id: nothing), suspends its sub-cluster at that edge: the rest of the sub-cluster's edges
+//     are flagged generic and decided by the event thread in order, with the full decision tree.
+// Same decisions, same float operations per merge as the one-thread walk; only independent work is
+// reordered.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned kEvNone = 0, kEvAbsorb = 1, kEvBB = 2;
+__device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, const uint32_t* codes, const uint32_t* pend_list,
+                           const int n_pend, unsigned char* done_flags) {
+  ScanShared& C = S.scan;
+  const float edge_w = (float)b * (float)(1.0 / (double)bucket_scale());
+  const bool force_bucket = edge_w < p.force_merge_weight;
+  const float y_gate = force_bucket ? p.y_force : p.y_merge;
+  const int mins = p.min_region_size;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  if (p.debug && tid == 0) t0 = clock64();
+  // shared-memory views (everything below aliases arrays that are free once the local ids are looked up)
+  unsigned char* const big = reinterpret_cast<unsigned char*>(C.tru);                  // [2 kScanMax] root is a hub (>= min size at staging)
+  unsigned char* const gen = reinterpret_cast<unsigned char*>(C.trv) + kScanMax;       // [kScanMax] edge is decided by the event thread, generic path
+  unsigned char* const evt = reinterpret_cast<unsigned char*>(C.trv) + 2 * kScanMax;   // [kScanMax] event type of the edge
+  unsigned short* const ev_a = C.hidx;                    // [kScanMax] hub on the region_1 side / absorbing hub
+  unsigned short* const ev_b = C.hidx + kScanMax;         // [kScanMax] hub on the region_2 side / absorbed piece
+  unsigned short* const owner = C.hidx + 2 * kScanMax;    // [2 kScanMax] small root: hub it sits in (0xFFFF = free; itself = promoted)
+  int* const sc = reinterpret_cast<int*>(C.hkey);         // [2 kScanMax] sub-cluster union-find over the small roots
+  unsigned* const keys = C.hkey + 2 * kScanMax;           // [kScanMax] (sub-cluster << 11 | edge index), sorted
+  unsigned short* const elist = reinterpret_cast<unsigned short*>(C.hkey + 3 * kScanMax);   // [kScanMax] edges the event thread looks at
+  // ---- staging: current roots of the edges -> compact local ids, records into shared memory ----
+  int hbits = 6;
+  while ((1 << hbits) < 4 * n_pend) ++hbits;
+  for (int i = tid; i < (1 << hbits); i += nthr) { C.hkey[i] = 0u; C.hidx[i] = 0xFFFFu; }
+  if (tid == 0) { C.n_roots = 0; C.hbits = hbits; }
+  __syncthreads();
+  for (int i = tid; i < n_pend; i += nthr) {
+    const uint32_t pos = pend_list[i];
+    int u, v;
+    decode_edge(p, codes[pos], u, v);
+    const int ru = uf_find(p.parent, u), rv = uf_find(p.parent, v);
+    C.epos[i] = pos;
+    C.tru[i] = ru; C.trv[i] = rv;
+    scan_insert(C, (unsigned)ru);
+    scan_insert(C, (unsigned)rv);
+  }
+  __syncthreads();
+  for (int i = tid; i < n_pend; i += nthr) {
+    C.ea[i] = scan_lookup(C, (unsigned)C.tru[i]);
+    C.eb[i] = scan_lookup(C, (unsigned)C.trv[i]);
+  }
+  __syncthreads();
+  const int n_roots = C.n_roots;
+  for (int j = tid; j < n_roots; j += nthr) {
+    C.par[j] = (unsigned short)j;
+    const RegionRec R = load_rec(&p.rec[C.gid[j]]);
+    scan_store(C.rec, j, R);
+    big[j] = R.sz >= mins ? 1 : 0;
+    owner[j] = 0xFFFFu;
+    sc[j] = j;
+  }
+  for (int i = tid; i < n_pend; i += nthr) { gen[i] = 0; evt[i] = kEvNone; }
+  __syncthreads();
+  // ---- sub-clusters: small roots joined by small-small edges ----
+  for (int i = tid; i < n_pend; i += nthr) {
+    const int a = C.ea[i], bq = C.eb[i];
+    if (a != bq && !big[a] && !big[bq]) cl_union(sc, a, bq);
+  }
+  __syncthreads();
+  int npad = 32;
+  while (npad < n_pend) npad <<= 1;
+  for (int i = tid; i < npad; i += nthr) {
+    unsigned key = 0xFFFFFFFFu;
+    if (i < n_pend) {
+      const int a = C.ea[i], bq = C.eb[i];
+      if (a != bq) {
+        if (big[a] && big[bq]) { evt[i] = kEvBB; ev_a[i] = (unsigned short)a; ev_b[i] = (unsigned short)bq; }
+        else key = ((unsigned)cl_find(sc, big[a] ? bq : a) << 11) | (unsigned)i;
+      }
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  // bitonic sort of the keys: a sub-cluster's edges end up next to each other, in reference order
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < npad / 2; t += nthr) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+        const unsigned x = keys[lo], y = keys[hi];
+        const bool up = ((lo & k) == 0);
+        if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+      }
+      __syncthreads();
+    }
+  if (p.debug && tid == 0) t1 = clock64();
+  // ---- one thread per sub-cluster: replay its edges in order ----
+  for (int q0 = tid; q0 < n_pend; q0 += nthr) {
+    const unsigned k0 = keys[q0];
+    if (k0 == 0xFFFFFFFFu) continue;
+    if (q0 > 0 && (keys[q0 - 1] >> 11) == (k0 >> 11)) continue;       // not the first edge of its sub-cluster
+    auto findl = [&](int x) { int q = C.par[x]; while (q != x) { const int g = C.par[q]; C.par[x] = (unsigned short)g; x = q; q = g; } return x; };
+    for (int q = q0; q < n_pend; ++q) {
+      const unsigned key = keys[q];
+      if ((key >> 11) != (k0 >> 11)) break;
+      const int i = (int)(key & 2047u);
+      const int ra = findl(C.ea[i]), rb = findl(C.eb[i]);
+      if (ra == rb) continue;
+      const int ha = big[ra] ? ra : (owner[ra] != 0xFFFFu ? (int)owner[ra] : -1);
+      const int hb = big[rb] ? rb : (owner[rb] != 0xFFFFu ? (int)owner[rb] : -1);
+      if (ha >= 0 && hb >= 0) {
+        if (ha != hb) { ev_a[i] = (unsigned short)ha; ev_b[i] = (unsigned short)hb; evt[i] = kEvBB; }
+        continue;
+      }
+      if (ha >= 0 || hb >= 0) {
+        const int h = ha >= 0 ? ha : hb, x = ha >= 0 ? rb : ra;
+        if (C.rec[x][0].y >= 0) {
+          // a constrained piece meets a hub: conditional on the hub's record -> the event thread takes over from here
+          for (int q2 = q; q2 < n_pend; ++q2) {
+            const unsigned k2 = keys[q2];
+            if ((k2 >> 11) != (k0 >> 11)) break;
+            gen[k2 & 2047u] = 1;
+          }
+          break;
+        }
+        ev_a[i] = (unsigned short)h; ev_b[i] = (unsigned short)x; evt[i] = kEvAbsorb;
+        owner[x] = (unsigned short)h;
+        continue;
+      }
+      RegionRec A = scan_load(C.rec, ra), B = scan_load(C.rec, rb);
+      const int r = decide_pair(p, A, B, edge_w);        // rep_1 = root of region_1 (the anchor), as in the reference
+      if (r != 2) scan_store(C.rec, ra, A);
+      if (r != 1) scan_store(C.rec, rb, B);
+      if (r == 1) { C.par[rb] = (unsigned short)ra; if (A.sz >= mins) owner[ra] = (unsigned short)ra; }
+      else if (r == 2) { C.par[ra] = (unsigned short)rb; if (B.sz >= mins) owner[rb] = (unsigned short)rb; }
+    }
+  }
+  __syncthreads();
+  if (p.debug && tid == 0) t2 = clock64();
+  // ---- edges with something for the event thread, in order ----
+  int n_ev = 0;
+  for (int base = 0; base < n_pend; base += nthr) {
+    const int i = base + tid;
+    const bool flag = i < n_pend && (evt[i] != kEvNone || gen[i]);
+    unsigned total;
+    const unsigned rank = block_rank(S, flag, &total);
+    if (flag) elist[n_ev + rank] = (unsigned short)i;
+    n_ev += (int)total;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    auto findl = [&](int x) { int q = C.par[x]; while (q != x) { const int g = C.par[q]; C.par[x] = (unsigned short)g; x = q; q = g; } return x; };
+    int cur = -1;                // hub whose record is held in registers
+    RegionRec H;
+    H.sz = 0; H.con = -1; H.d0 = H.d1 = H.d2 = 0.f; H.fin = 0; H.pad0 = H.pad1 = 0;
+    for (int e = 0; e < n_ev; ++e) {
+      const int i = elist[e];
+      if (gen[i]) {
+        if (cur >= 0) { scan_store(C.rec, cur, H); cur = -1; }
+        const int a = findl(C.ea[i]), bq = findl(C.eb[i]);
+        if (a == bq) continue;
+        RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
+        const int r = decide_pair(p, A, B, edge_w);
+        if (r != 2) scan_store(C.rec, a, A);
+        if (r != 1) scan_store(C.rec, bq, B);
+        if (r == 1) C.par[bq] = (unsigned short)a;
+        else if (r == 2) C.par[a] = (unsigned short)bq;
+        continue;
+      }
+      if (evt[i] == kEvAbsorb) {
+        const int h = findl(ev_a[i]), x = ev_b[i];
+        if (h != cur) { if (cur >= 0) scan_store(C.rec, cur, H); H = scan_load(C.rec, h); cur = h; }
+        const int2 x0 = C.rec[x][0], x1 = C.rec[x][1], x2 = C.rec[x][2];      // (sz, con) (d0, d1) (d2, fin); con < 0
+        const float xd0 = __int_as_float(x1.x), xd1 = __int_as_float(x1.y), xd2 = __int_as_float(x2.x);
+        if (!H.fin && !x2.y) {
+          // the test of segmentation_graph.h:377-390 on the squared distance (sqrtf is monotone; gates precomputed)
+          const float d1 = H.d0 - xd0, d2 = H.d1 - xd1, d3 = H.d2 - xd2;
+          const float y = (d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / 3.0f);
+          if (!(y < y_gate)) H.fin = 1;
+        }
+        // MergeRegions + MergeDescriptor: the hub is the bigger side (the piece is below min size)
+        const float denom = __frcp_rn((float)(x0.x + H.sz));
+        const float fa = (float)x0.x * denom, fb = (float)H.sz * denom;
+        H.d0 = fa * xd0 + fb * H.d0;
+        H.d1 = fa * xd1 + fb * H.d1;
+        H.d2 = fa * xd2 + fb * H.d2;
+        H.sz += x0.x;
+        C.par[x] = (unsigned short)h;
+        continue;
+      }
+      // two hubs meet
+      if (cur >= 0) { scan_store(C.rec, cur, H); cur = -1; }
+      const int a = findl(ev_a[i]), bq = findl(ev_b[i]);
+      if (a == bq) continue;
+      RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
+      const int r = decide_pair(p, A, B, edge_w);
+      if (r != 2) scan_store(C.rec, a, A);
+      if (r != 1) scan_store(C.rec, bq, B);
+      if (r == 1) C.par[bq] = (unsigned short)a;
+      else if (r == 2) C.par[a] = (unsigned short)bq;
+    }
+    if (cur >= 0) scan_store(C.rec, cur, H);
+    if (p.debug) t3 = clock64();
+  }
+  __syncthreads();
+  for (int j = tid; j < n_roots; j += nthr) {
+    int x = j;
+    while (C.par[x] != x) x = C.par[x];
+    const int g = C.gid[j];
+    if (x == j) store_rec(&p.rec[g], scan_load(C.rec, j));
+    else p.parent[g] = C.gid[x];
+  }
+  for (int i = tid; i < n_pend; i += nthr) done_flags[C.epos[i]] = 1;
+  if (tid == 0) atomicAdd(&p.stats[3], 1ull);
+  __syncthreads();
+  if (p.debug && tid == 0) {      // development tap: cycles per stage
+    atomicAdd(&p.debug[kNumBuckets * 4 + 50], (unsigned long long)(t3 - t2));       // event thread
+    atomicAdd(&p.debug[kNumBuckets * 4 + 51], (unsigned long long)(clock64() - t0));  // whole scan
+    atomicAdd(&p.debug[kNumBuckets * 4 + 52], (unsigned long long)n_roots);
+    atomicAdd(&p.debug[kNumBuckets * 4 + 53], (unsigned long long)(t1 - t0));       // staging + sub-clusters + sort
+    atomicAdd(&p.debug[kNumBuckets * 4 + 54], (unsigned long long)(t2 - t1));       // sub-cluster replay
+    atomicAdd(&p.debug[kNumBuckets * 4 + 55], (unsigned long long)n_ev);
+    atomicAdd(&p.debug[kNumBuckets * 4 + 56], (unsigned long long)n_pend);
+  }
 }
 
 struct RoundState { unsigned epoch, buf; bool from_master; unsigned long long n_src, prev_live; };
@@ -1308,7 +1558,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
                   __syncthreads();
                 }
                 for (unsigned long long q0 = 0; q0 < m; q0 += kScanMax)
-                  exact_scan(p, S.scan, b, codes, grp + q0, (int)min((unsigned long long)kScanMax, m - q0), p.done, -1, nullptr, nullptr);
+                  { const int nq = (int)min((unsigned long long)kScanMax, m - q0); if (p.dev_flags & 128) exact_scan(p, S.scan, b, codes, grp + q0, nq, p.done, -1, nullptr, nullptr); else split_scan(p, S, b, codes, grp + q0, nq, p.done); }
               }
               bar.sync();
             }
@@ -1317,7 +1567,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
           if (serial_tail && (!kIsGrid || blockIdx.x == 0)) {
             // the pending edges in reference order, kScanMax at a time (each batch reloads the current roots)
             for (unsigned long long q0 = 0; q0 < n_pend; q0 += kScanMax)
-              exact_scan(p, S.scan, b, codes, pend_list + q0, (int)min((unsigned long long)kScanMax, n_pend - q0), p.done, -1, nullptr, nullptr);
+              { const int nq = (int)min((unsigned long long)kScanMax, n_pend - q0); if (p.dev_flags & 128) exact_scan(p, S.scan, b, codes, pend_list + q0, nq, p.done, -1, nullptr, nullptr); else split_scan(p, S, b, codes, pend_list + q0, nq, p.done); }
           }
           bar.sync();
           if (p.debug && tid == 0 && blockIdx.x == 0) {
@@ -1479,6 +1729,23 @@ int launch_merge(const MergeParams& p_in, cudaStream_t s) {
   // came out at IoU 0.93 against the oracle (tests/gpu_debug_1080p.py; either switch alone restores the exact
   // partition), so the two stay development features (VSB200_MERGE_FLAGS=0) until the certificate is proven.
   p.dev_flags = getenv("VSB200_MERGE_FLAGS") ? atoi(getenv("VSB200_MERGE_FLAGS")) : 17;
+  {
+    // images of the two distance gates on the squared distance y (dist = sqrtf(y), correctly rounded on host and device):
+    // the smallest float y whose sqrtf fails the gate, found by bisection over the bit patterns of [0, 1]
+    auto gate = [](bool wide) {
+      auto pass = [wide](float y) { const float d = sqrtf(y); return wide ? ((double)d < 0.2) : (d < 0.05f); };
+      uint32_t lo = 0u, hi = 0x3f800000u;      // pass(0) holds, pass(1) fails
+      while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        float y; memcpy(&y, &mid, 4);
+        if (pass(y)) lo = mid; else hi = mid;
+      }
+      float y; memcpy(&y, &hi, 4);
+      return y;
+    };
+    p.y_merge = gate(false);
+    p.y_force = gate(true);
+  }
   int dev = 0, sms = 0, per_sm = 0;
   VSB_CUDA_OK(cudaGetDevice(&dev));
   VSB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -118,6 +118,9 @@ int vsb200_seg_reader_open(const char* filename, vsb200_seg_reader** out) {
   if (!f) { set_error("Could not open segmentation file %s", filename); return VSB200_ERR_INVALID; }
   vsb200_seg_reader* r = new vsb200_seg_reader;
   r->f = f;
+  long file_size = 0;
+  if (fseek(f, 0, SEEK_END) == 0) file_size = ftell(f);
+  fseek(f, 0, SEEK_SET);
   int32_t prev_header_id = -1;
   bool ok = true, said = false;
   while (ok) {                                                          // :178-226
@@ -136,6 +139,9 @@ int vsb200_seg_reader_open(const char* filename, vsb200_seg_reader** out) {
     if (strcmp(tag, "CHNK") != 0) { set_error("Parsing error, expected chunk header at current offset. Found: %s", tag); ok = false; said = true; break; }
     int32_t header_id = 0, n = 0;
     ok = fread(&header_id, 4, 1, f) == 1 && header_id == prev_header_id + 1 && fread(&n, 4, 1, f) == 1 && n >= 0;
+    // a chunk header lists n offsets and n time stamps (16 bytes per frame): a count the file cannot hold is corruption,
+    // not a reason to let std::vector throw through the C boundary
+    if (ok && (long long)n * 16 > (long long)file_size) ok = false;
     if (!ok) break;
     prev_header_id = header_id;
     const size_t base = r->file_offsets.size();
@@ -172,6 +178,22 @@ size_t vsb200_seg_reader_read(vsb200_seg_reader* r, int frame, uint8_t* buf, siz
   const size_t n = (size_t)size < cap ? (size_t)size : cap;
   if (buf && n && fread(buf, 1, n, r->f) != n) return 0;
   return (size_t)size;
+}
+
+int vsb200_seg_reader_read_frame(vsb200_seg_reader* r, int frame, uint8_t* buf, size_t cap, size_t* size_out) {
+  if (size_out) *size_out = 0;
+  if (!r || !size_out || frame < 0 || frame >= (int)r->file_offsets.size()) { set_error("reader: no such frame"); return VSB200_ERR_INVALID; }
+  char tag[5] = {0, 0, 0, 0, 0};
+  int32_t size = 0;
+  if (fseek(r->f, (long)r->file_offsets[frame], SEEK_SET) != 0 || fread(tag, 1, 4, r->f) != 4 || strcmp(tag, "SEGD") != 0 ||
+      fread(&size, 4, 1, r->f) != 1 || size < 0) {
+    set_error("Expecting segmentation header. Error parsing file.");      // :258-261
+    return VSB200_ERR_INVALID;
+  }
+  const size_t n = (size_t)size < cap ? (size_t)size : cap;
+  if (buf && n && fread(buf, 1, n, r->f) != n) { set_error("segmentation file is truncated inside frame %d", frame); return VSB200_ERR_INVALID; }
+  *size_out = (size_t)size;
+  return VSB200_OK;
 }
 
 void vsb200_seg_reader_close(vsb200_seg_reader* r) {

@@ -306,19 +306,40 @@ __global__ void __launch_bounds__(256) neighbor_pairs_rows_kernel(const int* __r
                                                                   unsigned long long* __restrict__ out,
                                                                   unsigned long long* __restrict__ out_count,
                                                                   unsigned long long out_cap) {
+  // The 256 voxels of a CTA meet a handful of distinct pairs, thousands of times: they are de-duplicated in a
+  // shared-memory hash first and only the distinct ones go to the global table (one dependent L2 access each).
+  constexpr unsigned kLocal = 512;
+  __shared__ unsigned long long stab[kLocal];
+  for (unsigned k = threadIdx.x; k < kLocal; k += blockDim.x) stab[k] = ~0ull;
+  __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;                     // slot * h + y
-  if (x >= w) return;
   const int slot = row / h, y = row - slot * h;
   const size_t base = (size_t)row * w;
   const int* r0 = roots + base;
   const int* l0 = labels + base;
+  auto local_insert = [&](int a, int b) {
+    const unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
+    const unsigned long long key = ((unsigned long long)lo << 32) | hi;
+    unsigned hsh = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40);
+    for (unsigned probe = 0; probe < 16; ++probe) {
+      const unsigned slot_ = (hsh + probe) & (kLocal - 1);
+      const unsigned long long cur = stab[slot_];
+      if (cur == key) return;
+      if (cur == ~0ull) {
+        const unsigned long long old = atomicCAS(&stab[slot_], ~0ull, key);
+        if (old == ~0ull || old == key) return;
+      }
+    }
+    pair_insert(table, cap_mask, a, b, out, out_count, out_cap);     // local table crowded: straight to the global one
+  };
+  if (x < w) {
   const int ra = __ldg(&r0[x]);
   int la = -1, last = -2;
 #define VSB_PAIR2(RP, LP, XX)                                                               \
   { const int rb = __ldg(&(RP)[XX]);                                                        \
     if (rb != ra) { if (la == -1) la = __ldg(&l0[x]); const int lb = __ldg(&(LP)[XX]);      \
-      if (lb != la && lb != last) { pair_insert(table, cap_mask, la, lb, out, out_count, out_cap); last = lb; } } }
+      if (lb != la && lb != last) { local_insert(la, lb); last = lb; } } }
   if (!(virtual_slot0 && slot == 0)) {
     if (x + 1 < w) VSB_PAIR2(r0, l0, x + 1)
     if (y + 1 < h) {
@@ -342,6 +363,12 @@ __global__ void __launch_bounds__(256) neighbor_pairs_rows_kernel(const int* __r
     }
   }
 #undef VSB_PAIR2
+  }
+  __syncthreads();
+  for (unsigned k = threadIdx.x; k < kLocal; k += blockDim.x) {
+    const unsigned long long key = stab[k];
+    if (key != ~0ull) pair_insert(table, cap_mask, (int)(key >> 32), (int)(key & 0xffffffffu), out, out_count, out_cap);
+  }
 }
 
 int launch_neighbor_pairs(const int* roots, const int* labels, int w, int h, int slots, const float* flows, int virtual_slot0,

@@ -75,14 +75,15 @@ class SegmentationReader:
         self._curr = frame
 
     def read_next_frame_binary(self) -> Optional[bytes]:
-        n = lib().vsb200_seg_reader_read(self._h, self._curr, None, 0)
-        if n == 0:
-            return None
-        buf = C.create_string_buffer(n)
-        if lib().vsb200_seg_reader_read(self._h, self._curr, buf, n) != n:
+        n = C.c_size_t()
+        if lib().vsb200_seg_reader_read_frame(self._h, self._curr, None, 0, C.byref(n)) != 0:
+            return None                           # parse error (vsb200_last_error says which)
+        buf = C.create_string_buffer(max(1, n.value))
+        got = C.c_size_t()
+        if lib().vsb200_seg_reader_read_frame(self._h, self._curr, buf, n.value, C.byref(got)) != 0 or got.value != n.value:
             return None
         self._curr += 1
-        return buf.raw
+        return buf.raw[:n.value]                  # b"" is a legitimately empty frame
 
     def close_file(self) -> None:
         if self._h:
