@@ -125,6 +125,16 @@ void vso_hist_normalize(const double* hist, const double* weight_sum, int n_regi
 /* ColorHistogram::ChiSquareDist (histograms.cpp:391-407) for region pairs [2 * n_pairs]. */
 void vso_hist_chisquare(const float* hist, int total_bins, const int32_t* pairs, int n_pairs, float* out);
 
+/* Hierarchical region stage (vso_hier.cpp): RegionSegmentation::ProcessFrame fed with the over-segmentation of the dense
+ * stage, frame by frame (segmentation/region_segmentation.cpp:97-205).  Results pop as flat int32 records in the layout
+ * of oracle/ref_hier_wrap.cpp (ref_hier_pop). */
+void* vso_hier_create(int width, int height, int use_flow, int chunk_set_size, int chunk_set_overlap, int constraint_chunks,
+                      int min_region_num, int max_region_num, float level_cutoff_fraction, float small_region_penalizer);
+int vso_hier_push(void* h, const vso_frame_result* overseg, const uint8_t* bgr, const float* flow_xy_or_null);
+int vso_hier_flush(void* h);
+long long vso_hier_pop(void* h, const int32_t** out);
+void vso_hier_destroy(void* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,3 +287,77 @@ class OracleDense:
             self.close()
         except Exception:
             pass
+
+
+def dict_to_result(d: dict):
+    """FrameResult over numpy arrays (the arrays are returned too: keep them alive while the struct is in use)."""
+    keep = dict(
+        region_id=np.ascontiguousarray(d["region_id"], np.int32),
+        interval_offset=np.ascontiguousarray(d["interval_offset"], np.int32),
+        intervals=np.ascontiguousarray(d["intervals"], np.int32).reshape(-1),
+        shape_moments=np.ascontiguousarray(d["shape_moments"], np.float32).reshape(-1),
+        compound=np.ascontiguousarray(d["compound"], np.int32).reshape(-1),
+        neighbor_offset=np.ascontiguousarray(d["neighbor_offset"], np.int32),
+        neighbor_id=np.ascontiguousarray(d["neighbor_id"], np.int32),
+    )
+    r = FrameResult()
+    for k in ("width", "height", "chunk_id", "chunk_size", "overlap_start", "hierarchy_frame_idx", "connectedness"):
+        setattr(r, k, int(d[k]))
+    r.pts = int(d.get("pts", 0))
+    r.n_regions = len(keep["region_id"])
+    r.n_compound = len(keep["compound"]) // 4
+    i32p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    for k in ("region_id", "interval_offset", "intervals", "compound", "neighbor_offset", "neighbor_id"):
+        setattr(r, k, keep[k].ctypes.data_as(i32p))
+    r.shape_moments = keep["shape_moments"].ctypes.data_as(f32p)
+    return r, keep
+
+
+class OracleHier:
+    """The oracle's hierarchical region stage (oracle/vso_hier.cpp), fed with over-segmentation results (dicts as
+    produced by OracleDense or by the product's DenseSegmentationUnit) plus the frames they belong to."""
+
+    def __init__(self, width, height, use_flow=False, chunk_set_size=6, chunk_set_overlap=2, constraint_chunks=1,
+                 min_region_num=10, max_region_num=10000, level_cutoff_fraction=0.8, small_region_penalizer=0.25):
+        L = lib()
+        L.vso_hier_create.restype = C.c_void_p
+        L.vso_hier_create.argtypes = [C.c_int] * 8 + [C.c_float, C.c_float]
+        L.vso_hier_push.argtypes = [C.c_void_p, C.POINTER(FrameResult), C.c_void_p, C.c_void_p]
+        L.vso_hier_flush.argtypes = [C.c_void_p]
+        L.vso_hier_pop.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32))]
+        L.vso_hier_pop.restype = C.c_longlong
+        L.vso_hier_destroy.argtypes = [C.c_void_p]
+        self._h = L.vso_hier_create(width, height, int(use_flow), chunk_set_size, chunk_set_overlap, constraint_chunks,
+                                    min_region_num, max_region_num, level_cutoff_fraction, small_region_penalizer)
+        if not self._h:
+            raise ValueError("vso_hier_create failed")
+
+    def _pop(self, n):
+        out = []
+        for _ in range(n):
+            p = C.POINTER(C.c_int32)()
+            nw = lib().vso_hier_pop(self._h, C.byref(p))
+            out.append(np.ctypeslib.as_array(p, shape=(nw,)).copy())
+        return out
+
+    def push(self, overseg: dict, bgr, flow=None):
+        r, keep = dict_to_result(overseg)
+        bgr = np.ascontiguousarray(bgr)
+        fl = None if flow is None else np.ascontiguousarray(flow, np.float32)
+        n = lib().vso_hier_push(self._h, C.byref(r), bgr.ctypes.data, None if fl is None else fl.ctypes.data)
+        del keep
+        return self._pop(n)
+
+    def flush(self):
+        return self._pop(lib().vso_hier_flush(self._h))
+
+    def close(self):
+        if self._h:
+            lib().vso_hier_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

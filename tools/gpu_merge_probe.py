@@ -27,7 +27,8 @@ if os.environ.get("PROBE_NO_ORACLE") is None:
     print("oracle %.1fs" % (time.time() - t0), flush=True)
 for fl in flags:
     os.environ["VSB200_MERGE_FLAGS"] = str(fl)
-    os.environ["VSB200_MERGE_DEBUG"] = "gpurun_out/%s_f%d_merge" % (tag, fl)
+    if os.environ.get("PROBE_NO_DEBUG") is None:
+        os.environ["VSB200_MERGE_DEBUG"] = "gpurun_out/%s_f%d_merge" % (tag, fl)
     u = DenseSegmentationUnit(want_id_maps=True)
     assert u.open_streams(w, h)
     got, per_chunk, prev = [], [], 0.0

@@ -295,10 +295,10 @@ constexpr int kScUncAny = 16;    // hub: may meet a hub with the same constraint
 #ifndef VSB_GROUP_SCAN_MIN
 #define VSB_GROUP_SCAN_MIN 1024
 #endif
-constexpr unsigned long long kWindowTarget = VSB_WINDOW_TARGET;   // live edges aimed at per window
+constexpr unsigned long long kWindowTargetDefault = VSB_WINDOW_TARGET;   // live edges aimed at per window
 constexpr unsigned long long kWindowMin = 4096;            // smallest raw window
-constexpr unsigned long long kSegmentMin = VSB_SEGMENT_MIN;           // segments are not halved below this many live edges
-constexpr unsigned long long kResidualSplit = VSB_RESIDUAL_SPLIT;        // uncertified edges that trigger a halving
+constexpr unsigned long long kSegmentMinDefault = VSB_SEGMENT_MIN;           // segments are not halved below this many live edges
+constexpr unsigned long long kResidualSplitDefault = VSB_RESIDUAL_SPLIT;        // uncertified edges that trigger a halving
 constexpr int kP1U = 8;                                     // edges per thread in flight in the prune pass
 
 // one atomic per converged group of lanes instead of one per live edge
@@ -783,59 +783,91 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
     n_ev += (int)total;
   }
   __syncthreads();
-  if (tid == 0) {
+  // ---- event thread(s): warp 0 walks the events in order.  The 32 lanes fetch 32 events (ids, the absorbed piece's
+  // record) at once; the events are then replayed one by one with the current hub's record held in registers by every
+  // lane (uniform, redundant arithmetic: the serial chain per absorb is a root lookup plus ~20 float operations);
+  // big-big and generic events are decided by lane 0 with the full decision tree. ----
+  if (tid < 32) {
+    const unsigned lane = tid;
     auto findl = [&](int x) { int q = C.par[x]; while (q != x) { const int g = C.par[q]; C.par[x] = (unsigned short)g; x = q; q = g; } return x; };
     int cur = -1;                // hub whose record is held in registers
     RegionRec H;
     H.sz = 0; H.con = -1; H.d0 = H.d1 = H.d2 = 0.f; H.fin = 0; H.pad0 = H.pad1 = 0;
-    for (int e = 0; e < n_ev; ++e) {
-      const int i = elist[e];
-      if (gen[i]) {
-        if (cur >= 0) { scan_store(C.rec, cur, H); cur = -1; }
-        const int a = findl(C.ea[i]), bq = findl(C.eb[i]);
-        if (a == bq) continue;
-        RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
-        const int r = decide_pair(p, A, B, edge_w);
-        if (r != 2) scan_store(C.rec, a, A);
-        if (r != 1) scan_store(C.rec, bq, B);
-        if (r == 1) C.par[bq] = (unsigned short)a;
-        else if (r == 2) C.par[a] = (unsigned short)bq;
-        continue;
-      }
-      if (evt[i] == kEvAbsorb) {
-        const int h = findl(ev_a[i]), x = ev_b[i];
-        if (h != cur) { if (cur >= 0) scan_store(C.rec, cur, H); H = scan_load(C.rec, h); cur = h; }
-        const int2 x0 = C.rec[x][0], x1 = C.rec[x][1], x2 = C.rec[x][2];      // (sz, con) (d0, d1) (d2, fin); con < 0
-        const float xd0 = __int_as_float(x1.x), xd1 = __int_as_float(x1.y), xd2 = __int_as_float(x2.x);
-        if (!H.fin && !x2.y) {
-          // the test of segmentation_graph.h:377-390 on the squared distance (sqrtf is monotone; gates precomputed)
-          const float d1 = H.d0 - xd0, d2 = H.d1 - xd1, d3 = H.d2 - xd2;
-          const float y = (d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / 3.0f);
-          if (!(y < y_gate)) H.fin = 1;
+    unsigned long long n_abs = 0, n_bb = 0, n_gen = 0, n_swap = 0;
+    for (int e0 = 0; e0 < n_ev; e0 += 32) {
+      const int cnt = min(32, n_ev - e0);
+      int my_i = 0, my_kind = 0, my_a = 0, my_b = 0, my_sz = 0, my_fin = 0;      // kind: 0 absorb, 1 big-big, 2 generic
+      float my_d0 = 0.f, my_d1 = 0.f, my_d2 = 0.f;
+      if ((int)lane < cnt) {
+        my_i = elist[e0 + lane];
+        if (gen[my_i]) { my_kind = 2; my_a = C.ea[my_i]; my_b = C.eb[my_i]; }
+        else {
+          my_a = ev_a[my_i]; my_b = ev_b[my_i];
+          if (evt[my_i] == kEvAbsorb) {
+            const int2 x0 = C.rec[my_b][0], x1 = C.rec[my_b][1], x2 = C.rec[my_b][2];      // (sz, con) (d0, d1) (d2, fin); con < 0
+            my_sz = x0.x; my_fin = x2.y;
+            my_d0 = __int_as_float(x1.x); my_d1 = __int_as_float(x1.y); my_d2 = __int_as_float(x2.x);
+          } else my_kind = 1;
         }
-        // MergeRegions + MergeDescriptor: the hub is the bigger side (the piece is below min size)
-        const float denom = __frcp_rn((float)(x0.x + H.sz));
-        const float fa = (float)x0.x * denom, fb = (float)H.sz * denom;
-        H.d0 = fa * xd0 + fb * H.d0;
-        H.d1 = fa * xd1 + fb * H.d1;
-        H.d2 = fa * xd2 + fb * H.d2;
-        H.sz += x0.x;
-        C.par[x] = (unsigned short)h;
-        continue;
       }
-      // two hubs meet
-      if (cur >= 0) { scan_store(C.rec, cur, H); cur = -1; }
-      const int a = findl(ev_a[i]), bq = findl(ev_b[i]);
-      if (a == bq) continue;
-      RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
-      const int r = decide_pair(p, A, B, edge_w);
-      if (r != 2) scan_store(C.rec, a, A);
-      if (r != 1) scan_store(C.rec, bq, B);
-      if (r == 1) C.par[bq] = (unsigned short)a;
-      else if (r == 2) C.par[a] = (unsigned short)bq;
+      for (int t = 0; t < cnt; ++t) {
+        const int kind = __shfl_sync(0xffffffffu, my_kind, t);
+        const int ea_ = __shfl_sync(0xffffffffu, my_a, t), eb_ = __shfl_sync(0xffffffffu, my_b, t);
+        if (kind == 0) {
+          const int xsz = __shfl_sync(0xffffffffu, my_sz, t), xfin = __shfl_sync(0xffffffffu, my_fin, t);
+          const float xd0 = __shfl_sync(0xffffffffu, my_d0, t), xd1 = __shfl_sync(0xffffffffu, my_d1, t), xd2 = __shfl_sync(0xffffffffu, my_d2, t);
+          const int h = findl(ea_);
+          if (h != cur) {
+            if (cur >= 0 && lane == 0) scan_store(C.rec, cur, H);
+            __syncwarp();
+            H = scan_load(C.rec, h);
+            cur = h;
+            ++n_swap;
+          }
+          if (!H.fin && !xfin) {
+            // the test of segmentation_graph.h:377-390 on the squared distance (sqrtf is monotone; gates precomputed)
+            const float d1 = H.d0 - xd0, d2 = H.d1 - xd1, d3 = H.d2 - xd2;
+            const float y = (d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / 3.0f);
+            if (!(y < y_gate)) H.fin = 1;
+          }
+          // MergeRegions + MergeDescriptor: the hub is the bigger side (the piece is below min size)
+          const float denom = __frcp_rn((float)(xsz + H.sz));
+          const float fa = (float)xsz * denom, fb = (float)H.sz * denom;
+          H.d0 = fa * xd0 + fb * H.d0;
+          H.d1 = fa * xd1 + fb * H.d1;
+          H.d2 = fa * xd2 + fb * H.d2;
+          H.sz += xsz;
+          if (lane == 0) C.par[eb_] = (unsigned short)h;
+          ++n_abs;
+          continue;
+        }
+        // big-big / generic: lane 0 with the full decision tree, on the records in shared memory
+        if (cur >= 0) { if (lane == 0) scan_store(C.rec, cur, H); cur = -1; }
+        if (lane == 0) {
+          const int a = findl(ea_), bq = findl(eb_);
+          if (a != bq) {
+            RegionRec A = scan_load(C.rec, a), B = scan_load(C.rec, bq);
+            const bool both_con = A.con >= 0 && B.con >= 0;
+            const bool nothing = (both_con && A.con != B.con) || (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+            if (!nothing) {
+              const int r = decide_pair(p, A, B, edge_w);        // rep_1 = root of region_1 (the anchor), as in the reference
+              if (r != 2) scan_store(C.rec, a, A);
+              if (r != 1) scan_store(C.rec, bq, B);
+              if (r == 1) C.par[bq] = (unsigned short)a;
+              else if (r == 2) C.par[a] = (unsigned short)bq;
+            }
+          }
+        }
+        __syncwarp();
+        if (kind == 1) ++n_bb; else ++n_gen;
+      }
     }
-    if (cur >= 0) scan_store(C.rec, cur, H);
-    if (p.debug) t3 = clock64();
+    if (cur >= 0 && lane == 0) scan_store(C.rec, cur, H);
+    if (p.debug && lane == 0) {
+      t3 = clock64();
+      atomicAdd(&p.debug[kNumBuckets * 4 + 57], n_abs); atomicAdd(&p.debug[kNumBuckets * 4 + 58], n_bb);
+      atomicAdd(&p.debug[kNumBuckets * 4 + 59], n_gen); atomicAdd(&p.debug[kNumBuckets * 4 + 60], n_swap);
+    }
   }
   __syncthreads();
   for (int j = tid; j < n_roots; j += nthr) {
@@ -993,6 +1025,7 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
   int wtag = (int)(*((volatile unsigned long long*)&p.counters[6]));
   bar.sync();                                   // everybody has read the persistent counters
   unsigned long long w0 = 0;
+  const unsigned long long kWindowTarget = p.window_target, kResidualSplit = p.residual_split, kSegmentMin = p.segment_min;
   unsigned long long target = kWindowTarget;   // live edges aimed at per window: grows while windows certify cleanly
   unsigned long long raw = min(bucket_edges, kWindowTarget);
   const bool tiny_windows = p.has_constraints && (p.dev_flags & 64);      // diagnostic: prune state (nearly) exact
@@ -1729,6 +1762,9 @@ int launch_merge(const MergeParams& p_in, cudaStream_t s) {
   // came out at IoU 0.93 against the oracle (tests/gpu_debug_1080p.py; either switch alone restores the exact
   // partition), so the two stay development features (VSB200_MERGE_FLAGS=0) until the certificate is proven.
   p.dev_flags = getenv("VSB200_MERGE_FLAGS") ? atoi(getenv("VSB200_MERGE_FLAGS")) : 17;
+  p.window_target = getenv("VSB200_WINDOW_TARGET") ? strtoull(getenv("VSB200_WINDOW_TARGET"), nullptr, 10) : kWindowTargetDefault;
+  p.residual_split = getenv("VSB200_RESIDUAL_SPLIT") ? strtoull(getenv("VSB200_RESIDUAL_SPLIT"), nullptr, 10) : kResidualSplitDefault;
+  p.segment_min = getenv("VSB200_SEGMENT_MIN") ? strtoull(getenv("VSB200_SEGMENT_MIN"), nullptr, 10) : kSegmentMinDefault;
   {
     // images of the two distance gates on the squared distance y (dist = sqrtf(y), correctly rounded on host and device):
     // the smallest float y whose sqrtf fails the gate, found by bisection over the bit patterns of [0, 1]
