@@ -42,6 +42,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "frames/sec 1080p dense over-seg"
 FRAMES_PER_STEP = 19          # new frames per chunk (chunk_size 20, 1 virtual + 1 constrained overlap)
 UNIQUE_FRAMES = 39            # generated frames per rank; longer runs ping-pong over them
+WORKLOAD = "BASELINE config 3 (dense half): {w}x{h} synthetic stream, dense over-segmentation, 20-slot constrained chunks"
 
 
 def edge_build_bytes(w, h):
@@ -113,39 +114,49 @@ def cpu_engine():
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (its DenseSegmentation::ProcessFrame
     stream compiled unmodified, oracle/Makefile; seg_tree_sample's decode / hierarchy / writer stages are outside the
-    path) on the box's host cores."""
+    path) on the box's host cores, on the SAME workload and step as the GPU arm: one continuous stream of the same
+    synthetic clip, a step = one constrained 20-slot chunk = 19 new frames.  The first (unconstrained, 20-frame) chunk
+    and min(W, 1) constrained chunks are warm-up; K constrained chunks are timed."""
     if rank != 0:
         return
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)          # torchrun pins it to 1; the reference's OpenMP loops want the cores
     from video_segment_b200.synth import synth
     w, h = args.width, args.height
     kind, make, cores = cpu_engine()
-    nfr = args.ref_frames
-    frames = list(synth(3, w, h, nfr))
-    def one_step():
-        o = make(w, h)
+    frames = list(synth(3, w, h, UNIQUE_FRAMES))
+    o = make(w, h)
+    k = 0
+    def step():
+        nonlocal k
         got = 0
-        for f in frames:
-            got += len(o.push(f))
-        got += len(o.flush())
-        o.close()
+        while got < FRAMES_PER_STEP:
+            got += len(o.push(frames[frame_index(k)]))
+            k += 1
         return got
-    for _ in range(min(args.warmup, 1)):      # CPU path: one warm-up pass is enough and keeps the run bounded
-        one_step()
+    for _ in range(1 + min(args.warmup, 1)):
+        step()
+    series = []
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        total += one_step()
+        t1 = time.perf_counter()
+        total += step()
+        series.append(round(1000.0 * (time.perf_counter() - t1), 1))
     dt = time.perf_counter() - t0
+    o.flush()           # untimed: the reference joins its graph-construction threads on flush, not in its destructor
+    o.close()
     fps = total / dt
-    sample = f"{nfr} frames of the {w}x{h} synthetic clip (seed 3) segmented as one flushed chunk per step"
+    sample = (f"one stream of the {w}x{h} synthetic clip (seed 3, ping-pong over {UNIQUE_FRAMES} frames): {args.steps} constrained chunks of "
+              f"{FRAMES_PER_STEP} new frames timed after the free first chunk")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w}x{h} synthetic, dense over-seg only (BASELINE config 3 without the hierarchical stage)",
-                   "step": sample, "threads": cores},
+        "config": {"workload": WORKLOAD.format(w=w, h=h), "step": f"one chunk = {FRAMES_PER_STEP} new frames", "threads": cores},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_step_series": series,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -159,7 +170,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--ref-frames", type=int, default=4, help="frames per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -178,6 +188,8 @@ def main():
     if not torch.cuda.is_available() or lib().vsb200_device_count() < 1:
         raise SystemExit("bench.py: no B200 / CUDA library -- this path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # O(#scan intervals) host shaping threads of the engine: the box's cores are shared by the ranks
+    os.environ.setdefault("VSB200_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w, h = args.width, args.height
@@ -198,23 +210,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    halo = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
-    halo_in = torch.empty((2, h, w), dtype=torch.int32, device="cuda")
+    # group seams: NCCL in the C++ host layer (csrc/shard.cu); the id travels over torch.distributed's store
+    from video_segment_b200.shard import SeamLink, nccl_unique_id
+    link = None
+    if world > 1:
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        link = SeamLink(uid[0], rank, world, local_rank, w, h)
+    first_map_dev = torch.zeros((h, w), dtype=torch.int32, device="cuda")
 
-    def seam_exchange(unit, first_map):
-        """C1: overlap id maps to the successor group; C2: all-gather of the region-id counts; then the
-        parallel-seam relabel of this group's ids by max-overlap voting in the shared frame (shard.py)."""
-        if world == 1:
-            return
-        from video_segment_b200.shard import relabel_table, seam_exchange as _seam, seam_vote
-        max_id = unit.export_halo(halo[0].data_ptr(), halo[1].data_ptr())[0]
-        got, offsets = _seam(halo, halo_in, max_id, rank, world)
-        if got is not None and first_map is not None:
-            try:
-                s_ids, p_ids, _ = seam_vote(got[1], first_map)
-                relabel_table(s_ids, p_ids, max_id + 1, offsets[rank]).cpu()  # the table a writer would apply
-            except Exception as e:                                            # bookkeeping only: never costs the measurement
-                print(f"bench.py: seam relabel failed on rank {rank}: {e}", file=sys.stderr)
+    EXCHANGE_EVERY = 5      # chunks per frame group: the seam hand-over runs at every group boundary inside the timed region
+
+    def seam_exchange(unit, have_first_map):
+        """Group boundary: C1 (overlap id maps to the successor, ncclSend / ncclRecv), C2 (all-gather of the region-id
+        counts), then the seam vote on the device -> relabel table of this group (what a writer applies to its ids)."""
+        if link is None:
+            return None
+        offsets = link.exchange(unit)
+        n_ids = max(1, offsets[rank + 1] - offsets[rank])
+        return link.relabel_table(first_map_dev.data_ptr() if have_first_map else 0, n_ids, offsets[rank])
 
     def run_leg(device_resident):
         unit = DenseSegmentationUnit(device=local_rank)
@@ -230,30 +244,37 @@ def main():
                 return unit.process_device_frame(dev_frames[i].data_ptr(), w * 3)
             return unit.process_frame(pinned[i].numpy())
         out_frames = 0
-        first_map = None             # this group's own segmentation of its first frame (shared with the predecessor)
+        have_first = False           # this group's own segmentation of its first frame (shared with the predecessor) is on the device
         # warm-up: W chunks (the first one takes 20 frames)
         while out_frames < FRAMES_PER_STEP * W:
             res = push_next()
-            if res and first_map is None and world > 1:
+            if res and not have_first and world > 1:
                 from video_segment_b200.unit import id_map_from_result
-                try:
-                    first_map = torch.from_numpy(id_map_from_result(res[0])).cuda()
-                except Exception as e:
-                    print(f"bench.py: could not render the seam frame on rank {rank}: {e}", file=sys.stderr)
-                    first_map = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+                first_map_dev.copy_(torch.from_numpy(id_map_from_result(res[0])))
+                have_first = True
             out_frames += len(res)
-        seam_exchange(unit, first_map)   # warm-up of the exchange too (NCCL opens its peer channels on first use)
+        seam_exchange(unit, have_first)  # warm-up of the exchange too (NCCL opens its peer channels on first use)
         st0, io0 = unit.stats(), unit.io_stats()
+        link0 = link.stats() if link else None
         sampler = ClockSampler(local_rank)
         barrier()
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        timed = 0
+        timed, chunks, series, regions, t_prev = 0, 0, [], [], t0
         while timed < FRAMES_PER_STEP * K:
-            timed += len(push_next())
-        seam_exchange(unit, first_map)
+            res = push_next()
+            if res:
+                timed += len(res)
+                chunks += 1
+                now = time.perf_counter()
+                series.append(round(1000.0 * (now - t_prev), 1))
+                regions.append(int(len(res[0]["region_id"])))
+                t_prev = now
+                if chunks % EXCHANGE_EVERY == 0 or timed >= FRAMES_PER_STEP * K:
+                    seam_exchange(unit, have_first)
+                    t_prev = time.perf_counter()
         torch.cuda.synchronize()
         e1.record()
         barrier()
@@ -261,13 +282,23 @@ def main():
         sampler.stop_flag = True
         ms = e0.elapsed_time(e1)
         st1, io1 = unit.stats(), unit.io_stats()
+        link1 = link.stats() if link else None
         unit.close()
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         d = {k2: st1[k2] - st0[k2] for k2 in st1}
         dio = {k2: io1[k2] - io0[k2] for k2 in io1}
-        return dict(ms=float(t.item()), wall=wall, frames=timed, stats=d, io=dio, clocks=sampler.summary())
+        mine = {"rank": rank, "ms": round(ms, 1), "merge_ms": round(d["merge_ms"], 1), "host_shape_ms": round(d["host_shape_ms"], 1),
+                "exchange_ms": round(link1["exchange_ms"] - link0["exchange_ms"], 2) if link else 0.0,
+                "exchanges": int(link1["exchanges"] - link0["exchanges"]) if link else 0}
+        per_rank = [mine]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            per_rank = gathered
+        return dict(ms=float(t.item()), wall=wall, frames=timed, stats=d, io=dio, clocks=sampler.summary(), series=series,
+                    regions=regions, per_rank=per_rank)
 
     leg_dev = run_leg(True)
     leg_e2e = run_leg(False)
@@ -295,8 +326,9 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": leg_dev["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (video_segment_b200.synth seed 3, 39 unique frames per GPU, ping-pong)",
-        "config": {"workload": f"{w}x{h} synthetic, dense over-seg only (BASELINE config 3 without the hierarchical stage)",
+        "config": {"workload": WORKLOAD.format(w=w, h=h),
                    "step": f"one chunk = {FRAMES_PER_STEP} new frames per GPU", "frames_per_gpu": FRAMES_PER_STEP * K,
+                   "seam_exchange": f"every {EXCHANGE_EVERY} chunks (csrc/shard.cu: ncclSend/ncclRecv + ncclAllGather, vote + relabel on the device)" if world > 1 else "none (1 GPU)",
                    "parallelism": f"frame-chunk groups x{world}", "l2": "inputs larger than L2: 21 slots x 24.9 MB frames + 2.3 GB edge weights per chunk"},
         "e2e": {"value": e2e, "unit": "frames/s",
                 "h2d_bytes_per_step": leg_e2e["io"]["h2d_bytes"] / K, "d2h_bytes_per_step": leg_e2e["io"]["d2h_bytes"] / K},
@@ -307,20 +339,22 @@ def main():
                      "bytes_per_launch": edge_build_bytes(w, h), "ms_per_launch": edge_ms, "launches_timed": int(io["edge_launches"])},
         "stage_ms_per_step": {k2: v / K for k2, v in leg_dev["stats"].items() if k2.endswith("_ms")},
         "merge_rounds_per_step": leg_dev["stats"]["merge_rounds"] / K,
+        "ms_per_step_series": leg_dev["series"], "regions_per_step": leg_dev["regions"],
+        "per_rank": leg_dev["per_rank"],
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind, make, cores = cpu_engine()
-        nfr = 8      # ~10 s of CPU work at 1080p (the reference costs ~1 s per frame; BASELINE asks for a bounded sample)
+        nfr = 1 + 2 * FRAMES_PER_STEP      # the free first chunk and one constrained chunk: ~20-30 s of CPU work at 1080p
         o = make(w, h)
         t0 = time.perf_counter()
         got = 0
-        for f in host_frames[:nfr]:
-            got += len(o.push(f))
+        for kf in range(nfr):
+            got += len(o.push(host_frames[frame_index(kf)]))
         got += len(o.flush())
         dt = time.perf_counter() - t0
         o.close()
         line["cpu_baseline"] = {"value": got / dt, "unit": "frames/s", "cores": cores, "kind": kind,
-                                "sample": f"first {nfr} frames of the same clip segmented as one flushed chunk ({dt:.1f} s)"}
+                                "sample": f"first {nfr} frames of the same stream: the free 20-frame chunk and one constrained chunk, flushed ({dt:.1f} s)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -191,6 +191,65 @@ int vsb200_region_hist_finish(const void* dev_scratch, int n_regions, int lum_bi
 int vsb200_hist_chisquare(const float* dev_hist, int total_bins, const int32_t* dev_pairs, int n_pairs,
                           float* dev_out, void* stream);
 
+/* ---- frame-group sharding over the GPUs of a box (csrc/shard.cu) ----
+ * One handle per rank.  NCCL is bound at run time (libnccl.so.2).  Replaces nothing in the reference (it has no
+ * multi-device path); the exchanged state is DenseSegmentation's chunk hand-over: overlap_segmentations_
+ * (dense_segmentation.cpp:300-328) and max_region_id_ (:360-365). */
+typedef struct vsb200_shard vsb200_shard;
+/* rank 0: ncclGetUniqueId; the 128 bytes go to the other ranks by any side channel. */
+int vsb200_shard_unique_id(uint8_t id_out[128]);
+int vsb200_shard_create(const uint8_t id[128], int rank, int world, int device, int width, int height, vsb200_shard** out);
+/* C1 + C2 at a group boundary (d stands right after a chunk boundary): overlap id maps to rank + 1 / from rank - 1
+ * (ncclSend / ncclRecv), all-gather of the region-id counts; id_offsets_out[world + 1] = exclusive prefix, last = total. */
+int vsb200_shard_exchange(vsb200_shard* s, vsb200_dense* d, int64_t* id_offsets_out, int* have_pred);
+/* the predecessor's two overlap id maps on the device ([2][h][w] int32), NULL on rank 0 / before an exchange */
+const int32_t* vsb200_shard_pred_maps(vsb200_shard* s);
+/* Seam vote on the device: own id map of the shared frame vs the predecessor's -> dev_table_out[n_ids]
+ * (local id -> predecessor id with the largest overlap, ids born later -> id_offset + id). */
+int vsb200_shard_vote(vsb200_shard* s, const int32_t* dev_own_first_map, int n_ids, int64_t id_offset, int32_t* dev_table_out);
+/* dev_ids[i] = dev_table[dev_ids[i]] for ids in [0, n_ids) */
+int vsb200_shard_relabel(vsb200_shard* s, int32_t* dev_ids, size_t n, const int32_t* dev_table, int n_ids);
+/* out: exchange ms on the device (sum), exchanges, kernel launches */
+void vsb200_shard_stats(vsb200_shard* s, double out[3]);
+void vsb200_shard_destroy(vsb200_shard* s);
+
+/* ---- hierarchical region stage (SURVEY section 8a config 3 + 8f N1; csrc/region_stage.cu) ----
+ * Plug point: RegionSegmentationUnit (segmentation/segmentation_unit.cpp:180-331) -> RegionSegmentation::ProcessFrame
+ * (segmentation/region_segmentation.cpp:97-205).  One handle per unit, driven by one thread. */
+typedef struct vsb200_region_opts {       /* RegionSegmentationOptions, segmentation/region_segmentation.h:41-82 */
+  int32_t min_region_num;                 /* 10 */
+  int32_t max_region_num;                 /* 10000 */
+  float level_cutoff_fraction;            /* 0.8 */
+  float small_region_penalizer;           /* 0.25 */
+  int32_t luminance_bins, color_bins, flow_bins;                       /* 10, 20, 16 */
+  int32_t chunk_set_size, chunk_set_overlap, constraint_chunks;        /* 6, 2, 1 */
+  int32_t save_descriptors;               /* 0; 1 -> VSB200_ERR_UNSUPPORTED */
+  int32_t use_appearance, use_flow, use_size_penalizer;                /* 1, 1 (a flow stream is present), 1 */
+  int32_t compute_vectorization;          /* 0; 1 -> VSB200_ERR_UNSUPPORTED */
+  int32_t device;
+} vsb200_region_opts;
+typedef struct vsb200_region vsb200_region;
+
+void vsb200_region_default_opts(vsb200_region_opts* o);
+/* RegionSegmentation::RegionSegmentation (region_segmentation.cpp:47-95); its CHECKs become VSB200_ERR_INVALID. */
+int vsb200_region_create(const vsb200_region_opts* o, int width, int height, vsb200_region** out);
+/* ProcessFrame(false, desc, features, results): one frame of the over-segmentation (the arrays a dense handle popped;
+ * n_compound > 0 marks the first frame of a dense chunk), its BGR24 host frame and, for flow streams, the frame's flow
+ * field (NULL on the first frame).  *n_ready = hierarchical frame results that became ready. */
+int vsb200_region_push(vsb200_region* r, const vsb200_frame_result* overseg, const uint8_t* bgr, int row_stride_bytes,
+                       const float* flow_xy, int flow_row_stride_bytes, int* n_ready);
+/* ProcessFrame(true, NULL, NULL, results) -- RegionSegmentationUnit::PostProcess. */
+int vsb200_region_flush(vsb200_region* r, int* n_ready);
+/* Next result as one flat int32 record (floats as bits), valid until the next pop; returns its length in words, 0 if
+ * nothing is ready:  width height chunk_id chunk_size overlap_start hierarchy_frame_idx n_regions n_levels |
+ * per region: id n_intervals (y left_x right_x)* 6 x shape moment | per hierarchy level: n_compound, per compound:
+ * id size parent_id start_frame end_frame n_neighbors n_children neighbor_id* child_id*   (SegmentationDesc,
+ * segment_util/segmentation.proto:55-172). */
+long long vsb200_region_pop(vsb200_region* r, const int32_t** record);
+/* out[0] = kernel launches so far, out[1] = chunk sets segmented */
+void vsb200_region_stats(vsb200_region* r, double out[2]);
+void vsb200_region_destroy(vsb200_region* r);
+
 /* ---- result container (csrc/pb_io.cpp, host only) ----
  * The reference's segmentation file, segment_util/segmentation_io.cpp: "HEAD" int32 n, n x int32 | per chunk "CHNK"
  * int32 chunk_id, int32 n_frames, n x int64 absolute frame offsets, n x int64 pts, int64 offset of the next header,

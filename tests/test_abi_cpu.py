@@ -103,4 +103,5 @@ def test_reference_arm_prints_one_line_under_torchrun():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "frames/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["higher_is_better"] is True and line["config"]["workload"].startswith("160x120")
+    assert line["higher_is_better"] is True and "160x120" in line["config"]["workload"]
+    assert len(line["ms_per_step_series"]) == 1

@@ -22,6 +22,19 @@ class DenseOpts(C.Structure):
     ]
 
 
+class RegionOpts(C.Structure):
+    """vsb200_region_opts (include/vsb200.h) == RegionSegmentationOptions
+    (reference segmentation/region_segmentation.h:41-82)."""
+    _fields_ = [
+        ("min_region_num", C.c_int32), ("max_region_num", C.c_int32),
+        ("level_cutoff_fraction", C.c_float), ("small_region_penalizer", C.c_float),
+        ("luminance_bins", C.c_int32), ("color_bins", C.c_int32), ("flow_bins", C.c_int32),
+        ("chunk_set_size", C.c_int32), ("chunk_set_overlap", C.c_int32), ("constraint_chunks", C.c_int32),
+        ("save_descriptors", C.c_int32), ("use_appearance", C.c_int32), ("use_flow", C.c_int32),
+        ("use_size_penalizer", C.c_int32), ("compute_vectorization", C.c_int32), ("device", C.c_int32),
+    ]
+
+
 class FrameResult(C.Structure):
     """vsb200_frame_result (include/vsb200.h)."""
     _fields_ = [
@@ -53,6 +66,10 @@ EXPORTED_SYMBOLS = [
     "vsb200_seg_writer_close", "vsb200_seg_reader_open", "vsb200_seg_reader_num_frames", "vsb200_seg_reader_num_header_flags",
     "vsb200_seg_reader_header_flags", "vsb200_seg_reader_time_stamps", "vsb200_seg_reader_read", "vsb200_seg_reader_read_frame", "vsb200_seg_reader_close",
     "vsb200_strip_to_essentials", "vsb200_encode_frame_proto",
+    "vsb200_region_default_opts", "vsb200_region_create", "vsb200_region_push", "vsb200_region_flush", "vsb200_region_pop",
+    "vsb200_region_stats", "vsb200_region_destroy",
+    "vsb200_shard_unique_id", "vsb200_shard_create", "vsb200_shard_exchange", "vsb200_shard_pred_maps", "vsb200_shard_vote",
+    "vsb200_shard_relabel", "vsb200_shard_stats", "vsb200_shard_destroy",
 ]
 
 _lib = None
@@ -114,6 +131,21 @@ def lib() -> C.CDLL:
         "vsb200_seg_reader_close": ([vp], None),
         "vsb200_strip_to_essentials": ([vp, C.c_int, vp, C.c_size_t], C.c_size_t),
         "vsb200_encode_frame_proto": ([vp, vp, C.c_size_t], C.c_size_t),
+        "vsb200_region_default_opts": ([C.POINTER(RegionOpts)], None),
+        "vsb200_region_create": ([C.POINTER(RegionOpts), C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
+        "vsb200_region_push": ([vp, C.POINTER(FrameResult), vp, C.c_int, vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
+        "vsb200_region_flush": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "vsb200_region_pop": ([vp, C.POINTER(C.POINTER(C.c_int32))], C.c_longlong),
+        "vsb200_region_stats": ([vp, C.POINTER(C.c_double)], None),
+        "vsb200_region_destroy": ([vp], None),
+        "vsb200_shard_unique_id": ([vp], C.c_int),
+        "vsb200_shard_create": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
+        "vsb200_shard_exchange": ([vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)], C.c_int),
+        "vsb200_shard_pred_maps": ([vp], vp),
+        "vsb200_shard_vote": ([vp, vp, C.c_int, C.c_int64, vp], C.c_int),
+        "vsb200_shard_relabel": ([vp, vp, C.c_size_t, vp, C.c_int], C.c_int),
+        "vsb200_shard_stats": ([vp, C.POINTER(C.c_double)], None),
+        "vsb200_shard_destroy": ([vp], None),
     }
     missing = []
     for name, (argtypes, restype) in sigs.items():

@@ -315,24 +315,28 @@ int vsb200_dense::chunk_boundary(bool flush_all, int* n_ready) {
   return 0;
 }
 
-// MergeConstrainedRegions (segmentation_graph.h:703-786), host assisted: the device lists the
-// distinct representatives met on the constrained slot in first-occurrence order; the O(#regions)
-// decision walk runs on the host and its unions / constraint resets are written back.
+// MergeConstrainedRegions (segmentation_graph.h:703-786), host assisted.  The reference walks every non-virtual node
+// whose OWN (possibly stale) record still carries a constraint id, in node order, and handles the node's current
+// representative: look its constraint id up in a map; insert it, or merge with / split from the map's holder.  Repeated
+// visits of one representative with nothing in between are idempotent from the fourth on, so the device lists, in node
+// order, the first four nodes of every run of visited nodes with one representative (O(#scan runs) records) and the
+// host replays exactly those visits; then the virtual nodes, which always merge (:763-785).
 namespace {
-__global__ void mcr_first_kernel(const int* __restrict__ labels_slot1, int base, int n, int* __restrict__ first) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicMin(&first[labels_slot1[i]], base + i);
-}
-__global__ void mcr_collect_kernel(const int* __restrict__ labels_slot1, int base, int n, int* __restrict__ first,
-                                   int2* __restrict__ out, unsigned* __restrict__ count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int r = labels_slot1[i];
-  if (first[r] == base + i) {
+__global__ void mcr_visits_kernel(const int* __restrict__ labels, const RegionRec* __restrict__ rec, int base, long long total,
+                                  int2* __restrict__ out, unsigned* __restrict__ count, unsigned cap) {
+  for (long long i = base + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (rec[i].con < 0) continue;
+    const int root = labels[i];
+    int pos = 0;                                  // position inside the run of visited nodes with this representative
+    while (pos < 4 && i - pos - 1 >= base && rec[i - pos - 1].con >= 0 && labels[i - pos - 1] == root) ++pos;
+    if (pos >= 4) continue;
     const unsigned k = atomicAdd(count, 1u);
-    out[k] = make_int2(base + i, r);
-    first[r] = 0x7f7f7f7f;      // restore scratch
+    if (k < cap) out[k] = make_int2((int)i, root);
   }
+}
+__global__ void gather_i32_kernel(const int* __restrict__ ids, int m, const int* __restrict__ src, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = src[ids[i]];
 }
 __global__ void gather_rec_kernel(const int* __restrict__ ids, int m, const RegionRec* __restrict__ rec, RegionRec* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,44 +346,68 @@ __global__ void scatter_rec_kernel(const int* __restrict__ ids, const int* __res
                                    const RegionRec* __restrict__ recs, RegionRec* __restrict__ rec, int* __restrict__ parent) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  rec[ids[i]] = recs[i];
+  // only the merge-relevant fields of a representative change here; a node's own stale constraint id stays as it is
+  RegionRec r = recs[i];
+  rec[ids[i]] = r;
   parent[ids[i]] = parents[i];
 }
 }  // namespace
 
 int vsb200_dense::merge_constrained_regions(int slots) {
-  // roots of slot 1 nodes
-  ENG_RC(launch_flatten(d_parent, nullptr, d_labels, (long long)n * 2, stream));     // slots 0 and 1
-  int* first = mp.cl;   // scratch (identity outside a merge launch) -> use hull flags instead? use d_size_adjust
-  first = d_size_adjust;
-  ENG_CUDA(cudaMemsetAsync(first, 0x7f, ((size_t)n * slots + 1) * sizeof(int), stream));
-  int2* d_list = (int2*)d_runs;   // runs buffer is free at this point
+  const long long total = (long long)n * slots;
+  ENG_RC(launch_flatten(d_parent, nullptr, d_labels, total, stream));
+  // visit records: at most four per scan run of the label volume; sized generously, grown on overflow
   if (runs_cap < (size_t)n) {
     if (d_runs) cudaFree(d_runs);
     runs_cap = (size_t)n * 2;
     ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
-    d_list = (int2*)d_runs;
   }
-  ENG_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned), stream));
-  mcr_first_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_labels + n, n, n, first);
-  mcr_collect_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_labels + n, n, n, first, d_list, d_total);
   unsigned cnt = 0;
-  ENG_CUDA(cudaMemcpyAsync(&cnt, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-  ENG_CUDA(cudaStreamSynchronize(stream));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const unsigned cap = (unsigned)std::min<size_t>(runs_cap * sizeof(RunRec) / sizeof(int2), 0x7fffffffu);
+    ENG_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned), stream));
+    mcr_visits_kernel<<<148 * 8, 256, 0, stream>>>(d_labels, d_rec, n, total, (int2*)d_runs, d_total, cap);
+    ENG_CUDA(cudaMemcpyAsync(&cnt, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    ENG_CUDA(cudaStreamSynchronize(stream));
+    if (cnt <= cap) break;
+    cudaFree(d_runs);
+    runs_cap = ((size_t)cnt * sizeof(int2) / sizeof(RunRec) + 1) * 2;
+    ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
+  }
   std::vector<int2> list(cnt);
-  if (cnt) ENG_CUDA(cudaMemcpy(list.data(), d_list, sizeof(int2) * cnt, cudaMemcpyDeviceToHost));
+  if (cnt) ENG_CUDA(cudaMemcpy(list.data(), d_runs, sizeof(int2) * cnt, cudaMemcpyDeviceToHost));
+  d2h_bytes += 8.0 * cnt;
   std::sort(list.begin(), list.end(), [](const int2& a, const int2& b) { return a.x < b.x; });
-  // virtual representatives: first pixel of every constraint id on slot 0 (from the overlap result)
-  std::vector<int> ids;          // device node ids whose records take part
+  std::vector<int> ids;               // device node ids whose records take part
   std::unordered_map<int, int> pos;   // node id -> local index
+  pos.reserve(1 << 14);
   auto local = [&](int id) { auto it = pos.find(id); if (it != pos.end()) return it->second; pos[id] = (int)ids.size(); ids.push_back(id); return (int)ids.size() - 1; };
-  for (const auto& e : list) local(e.y);
-  std::vector<std::pair<int, int>> virt;   // (constraint id, local index of virtual rep)
+  std::vector<int> visit_rep(cnt);
+  for (unsigned k = 0; k < cnt; ++k) visit_rep[k] = local(list[k].y);
+  std::vector<std::pair<int, int>> virt;   // (constraint id, local index of the virtual representative), first pixel of every id on slot 0
   {
     std::vector<int> h_first((size_t)max_region_id + 1);
     ENG_CUDA(cudaMemcpy(h_first.data(), d_first_of_id, sizeof(int) * ((size_t)max_region_id + 1), cudaMemcpyDeviceToHost));
+    // the virtual representative's CURRENT representative (virtual nodes merge during the scan like any other node)
+    std::vector<int> want;
+    for (int c = 0; c <= max_region_id; ++c) if (h_first[c] != 0x7f7f7f7f) want.push_back(h_first[c]);
+    std::vector<int> roots(want.size());
+    if (!want.empty()) {
+      if (tmp_cap < want.size()) {
+        if (d_tmp_ids) cudaFree(d_tmp_ids);
+        if (d_tmp_info) cudaFree(d_tmp_info);
+        tmp_cap = want.size() * 2 + 1024;
+        ENG_CUDA(cudaMalloc(&d_tmp_ids, tmp_cap * 2 * sizeof(int)));
+        ENG_CUDA(cudaMalloc(&d_tmp_info, tmp_cap * sizeof(RegionRec)));
+      }
+      ENG_CUDA(cudaMemcpyAsync(d_tmp_ids, want.data(), sizeof(int) * want.size(), cudaMemcpyHostToDevice, stream));
+      gather_i32_kernel<<<(unsigned)((want.size() + 255) / 256), 256, 0, stream>>>(d_tmp_ids, (int)want.size(), d_labels, d_tmp_ids + tmp_cap);
+      ENG_CUDA(cudaMemcpyAsync(roots.data(), d_tmp_ids + tmp_cap, sizeof(int) * want.size(), cudaMemcpyDeviceToHost, stream));
+      ENG_CUDA(cudaStreamSynchronize(stream));
+    }
+    size_t k = 0;
     for (int c = 0; c <= max_region_id; ++c)
-      if (h_first[c] != 0x7f7f7f7f) virt.emplace_back(c, local(h_first[c]));
+      if (h_first[c] != 0x7f7f7f7f) virt.emplace_back(c, local(roots[k++]));
   }
   const int m = (int)ids.size();
   if (m == 0) return 0;
@@ -403,6 +431,8 @@ int vsb200_dense::merge_constrained_regions(int slots) {
     const float d1 = a.d0 - b.d0, d2 = a.d1 - b.d1, d3 = a.d2 - b.d2;
     return std::sqrt((d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / 3.0f));   // edge weight 1.0: no force merge
   };
+  unsigned long long version = 1;                    // bumped by every change of the walk's state
+  std::vector<unsigned long long> settled(m, 0);     // version at which a representative was last found to be a no-op
   auto merge = [&](int a, int b) {                 // MergeRegions(rep_1 = a, rep_2 = b)
     const bool aw = recs[a].sz > recs[b].sz;
     const int mi = aw ? a : b, oi = aw ? b : a;
@@ -414,31 +444,33 @@ int vsb200_dense::merge_constrained_regions(int slots) {
     M.sz += O.sz;
     M.con = std::max(recs[a].con, recs[b].con);
     par[oi] = mi;
+    ++version;
   };
   std::unordered_map<int, int> con2rep;
   auto visit = [&](int my) {
     // one step of the non-virtual loop (:722-760) for representative `my`
+    if (settled[my] == version) return;               // nothing changed since this representative was last a no-op
     auto it = con2rep.find(recs[my].con);
-    if (it == con2rep.end()) { con2rep[recs[my].con] = my; return; }
+    if (it == con2rep.end()) { con2rep[recs[my].con] = my; ++version; settled[my] = version; return; }
     const int cr = find(it->second);
-    if (cr == my) return;
+    if (cr == my) { settled[my] = version; return; }
     const float d = dist(recs[my], recs[cr]);
     if (d > 0.15f) {
-      if ((double)recs[my].sz < (double)recs[cr].sz * 0.3) recs[my].con = -1;
-      else if ((double)recs[cr].sz < (double)recs[my].sz * 0.3) { recs[cr].con = -1; it->second = my; }
-      else { recs[my].con = -1; recs[cr].con = -1; con2rep.erase(it); }
+      bool changed = false;
+      if ((double)recs[my].sz < (double)recs[cr].sz * 0.3) {
+        if (recs[my].con != -1) { recs[my].con = -1; changed = true; }
+      } else if ((double)recs[cr].sz < (double)recs[my].sz * 0.3) {
+        if (recs[cr].con != -1) { recs[cr].con = -1; changed = true; }
+        if (it->second != my) { it->second = my; changed = true; }
+      } else {
+        recs[my].con = -1; recs[cr].con = -1; con2rep.erase(it); changed = true;
+      }
+      if (changed) ++version; else settled[my] = version;     // unchanged: the same comparison would only repeat itself
     } else {
       merge(my, cr);
     }
   };
-  for (const auto& e : list) {
-    int my = find(pos[e.y]);
-    const int before = recs[my].con;
-    visit(my);
-    my = find(my);
-    // a representative that lost its constraint is looked up again under key -1 by its next node
-    if (before >= 0 && recs[my].con < 0) visit(my);
-  }
+  for (unsigned k = 0; k < cnt; ++k) visit(find(visit_rep[k]));
   for (const auto& v : virt) {                        // virtual nodes: always merge (:763-785)
     const int my = find(v.second);
     auto it = con2rep.find(recs[my].con);
@@ -452,7 +484,7 @@ int vsb200_dense::merge_constrained_regions(int slots) {
   ENG_CUDA(cudaMemcpyAsync(d_recs, recs.data(), sizeof(RegionRec) * m, cudaMemcpyHostToDevice, stream));
   scatter_rec_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_tmp_ids, d_tmp_ids + tmp_cap, m, d_recs, d_rec, d_parent);
   ENG_CUDA(cudaStreamSynchronize(stream));
-  stats[7] += 5;
+  stats[7] += 4;
   return 0;
 }
 

@@ -16,6 +16,7 @@
 
 #include "../../include/vsb200.h"
 #include "common.cuh"
+#include "region_kernels.cuh"
 
 #define LAB_TAB_QUAL __device__ const
 #include "lab_tables.inc"
@@ -166,6 +167,14 @@ static int grid_for(size_t work_items, int block) {
   const size_t want = (work_items + block - 1) / block;
   const size_t cap = (size_t)sms * 8;                       // a multiple of the SM count; grid-stride loops cover the rest
   return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+int launch_region_hist(const uint8_t* dev_bgr, int row_stride_bytes, const int* dev_region_ids, int w, int h, int n_regions,
+                       int lum_bins, int color_bins, unsigned long long* acc, unsigned* cnt, cudaStream_t s) {
+  region_hist_kernel<<<grid_for((size_t)w * h, 256), 256, 0, s>>>(dev_bgr, row_stride_bytes, dev_region_ids, w, h, n_regions, lum_bins,
+                                                                   color_bins, acc, cnt);
+  VSB_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace vsb

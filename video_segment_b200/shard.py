@@ -89,3 +89,98 @@ def relabel_table(succ_ids: torch.Tensor, pred_ids: torch.Tensor, num_succ_ids: 
     table = torch.arange(num_succ_ids, dtype=torch.int64, device=succ_ids.device) + int(id_offset)
     table[succ_ids] = pred_ids
     return table
+
+
+# ---------------------------------------------------------------------------------------------
+# The product's seam hand-over: NCCL in the C++ host layer (csrc/shard.cu, vsb200_shard_*), vote and relabel on the
+# device.  torch is not involved; the functions above remain as the backend-agnostic statement of C1 / C2 that the CPU
+# tests exercise on gloo.
+# ---------------------------------------------------------------------------------------------
+import ctypes as _C
+
+import numpy as _np
+
+
+def nccl_unique_id() -> bytes:
+    """Rank 0: the 128-byte NCCL id the other ranks need for SeamLink (send it over any side channel)."""
+    from ._lib import check, lib
+    buf = (_C.c_uint8 * 128)()
+    check(lib().vsb200_shard_unique_id(buf), "vsb200_shard_unique_id")
+    return bytes(buf)
+
+
+class SeamLink:
+    """One rank's end of the group seams: vsb200_shard_* over a DenseSegmentationUnit."""
+
+    def __init__(self, unique_id: Optional[bytes], rank: int, world: int, device: int, width: int, height: int):
+        from ._lib import check, lib
+        self._h = _C.c_void_p()
+        self.rank, self.world, self.w, self.h = rank, world, width, height
+        idbuf = (_C.c_uint8 * 128)(*unique_id) if unique_id else None
+        check(lib().vsb200_shard_create(idbuf, rank, world, device, width, height, _C.byref(self._h)), "vsb200_shard_create")
+        self._table = None
+        self._keep = None
+
+    def exchange(self, unit) -> List[int]:
+        """C1 + C2 at a group boundary of `unit` (right after a chunk boundary).  Returns the exclusive prefix of the
+        groups' region-id counts, world + 1 entries (offsets[rank + 1] - offsets[rank] = this group's count)."""
+        from ._lib import check, lib
+        offs = (_C.c_int64 * (self.world + 1))()
+        have = _C.c_int()
+        check(lib().vsb200_shard_exchange(self._h, unit._h, offs, _C.byref(have)), "vsb200_shard_exchange")
+        self.have_pred = bool(have.value)
+        return [int(v) for v in offs]
+
+    def relabel_table(self, own_first_map_dev_ptr: int, n_ids: int, id_offset: int) -> "_np.ndarray":
+        """Vote on the device; returns the table (host copy, int32 [n_ids]); a device copy stays for relabel()."""
+        import torch
+        from ._lib import check, lib
+        table = torch.empty(n_ids, dtype=torch.int32, device="cuda")
+        check(lib().vsb200_shard_vote(self._h, _C.c_void_p(own_first_map_dev_ptr), n_ids, id_offset, _C.c_void_p(table.data_ptr())),
+              "vsb200_shard_vote")
+        self._table = table
+        return table.cpu().numpy()
+
+    def relabel_device(self, ids_dev_ptr: int, n: int) -> None:
+        from ._lib import check, lib
+        check(lib().vsb200_shard_relabel(self._h, _C.c_void_p(ids_dev_ptr), n, _C.c_void_p(self._table.data_ptr()), int(self._table.numel())),
+              "vsb200_shard_relabel")
+
+    def stats(self) -> dict:
+        from ._lib import lib
+        a = (_C.c_double * 3)()
+        lib().vsb200_shard_stats(self._h, a)
+        return dict(exchange_ms=a[0], exchanges=a[1], kernel_launches=a[2])
+
+    def close(self):
+        if self._h:
+            from ._lib import lib
+            lib().vsb200_shard_destroy(self._h)
+            self._h = _C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def relabel_results(results: List[dict], table: "_np.ndarray") -> None:
+    """Applies a relabel table to the per-region / per-compound id arrays of frame results, in place (ids beyond the
+    table are left alone); regions and compounds are re-sorted by id where the reference's constrained output is."""
+    n = len(table)
+
+    def m(a):
+        a = _np.asarray(a)
+        out = a.copy()
+        ok = (a >= 0) & (a < n)
+        out[ok] = table[a[ok]]
+        return out
+    for r in results:
+        r["region_id"] = m(r["region_id"]).astype(_np.int32)
+        if "id_map" in r and r["id_map"] is not None:
+            r["id_map"] = m(r["id_map"]).astype(_np.int32)
+        if len(r.get("compound", [])):
+            r["compound"] = r["compound"].copy()
+            r["compound"][:, 0] = m(r["compound"][:, 0])
+            r["neighbor_id"] = m(r["neighbor_id"]).astype(_np.int32)

@@ -239,3 +239,175 @@ def id_map_from_result(d: dict) -> np.ndarray:
         for y, lx, rx in d["intervals"][off[k]:off[k + 1]]:
             img[y, lx:rx + 1] = rid
     return img
+
+
+# ---------------------------------------------------------------------------------------------
+# RegionSegmentationUnit (reference segmentation/segmentation_unit.h:126-190, segmentation_unit.cpp:180-331)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class RegionSegmentationOptions:
+    """Field-for-field RegionSegmentationOptions (segmentation/region_segmentation.h:41-82)."""
+    min_region_num: int = 10
+    max_region_num: int = 10000
+    level_cutoff_fraction: float = 0.8
+    small_region_penalizer: float = 0.25
+    luminance_bins: int = 10
+    color_bins: int = 20
+    flow_bins: int = 16
+    chunk_set_size: int = 6
+    chunk_set_overlap: int = 2
+    constraint_chunks: int = 1
+    save_descriptors: bool = False
+    use_appearance: bool = True
+    use_flow: bool = True
+    use_size_penalizer: bool = True
+    compute_vectorization: bool = False      # the reference defaults to True (cv::approxPolyDP, SURVEY row N3: not built)
+
+
+def _dict_to_result(d: dict):
+    """vsb200_frame_result over the arrays of an over-segmentation result dict (kept alive by the caller)."""
+    keep = dict(
+        region_id=np.ascontiguousarray(d["region_id"], np.int32),
+        interval_offset=np.ascontiguousarray(d["interval_offset"], np.int32),
+        intervals=np.ascontiguousarray(d["intervals"], np.int32).reshape(-1),
+        shape_moments=np.ascontiguousarray(d["shape_moments"], np.float32).reshape(-1),
+        compound=np.ascontiguousarray(d["compound"], np.int32).reshape(-1),
+        neighbor_offset=np.ascontiguousarray(d["neighbor_offset"], np.int32),
+        neighbor_id=np.ascontiguousarray(d["neighbor_id"], np.int32),
+    )
+    r = FrameResult()
+    for k in ("width", "height", "chunk_id", "chunk_size", "overlap_start", "hierarchy_frame_idx", "connectedness"):
+        setattr(r, k, int(d[k]))
+    r.pts = int(d.get("pts", 0))
+    r.n_regions = len(keep["region_id"])
+    r.n_compound = len(keep["compound"]) // 4
+    i32p, f32p = C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    for k in ("region_id", "interval_offset", "intervals", "compound", "neighbor_offset", "neighbor_id"):
+        setattr(r, k, keep[k].ctypes.data_as(i32p))
+    r.shape_moments = keep["shape_moments"].ctypes.data_as(f32p)
+    return r, keep
+
+
+def parse_region_record(rec: np.ndarray) -> dict:
+    """Flat record of vsb200_region_pop -> SegmentationDesc fields: over-segmentation of the frame plus, on the first
+    frame of a chunk set, the hierarchy levels (lists of dicts id / size / parent_id / start_frame / end_frame /
+    neighbors / children)."""
+    d = dict(zip(("width", "height", "chunk_id", "chunk_size", "overlap_start", "hierarchy_frame_idx"), map(int, rec[:6])))
+    n_regions, n_levels = int(rec[6]), int(rec[7])
+    pos = 8
+    ids, offs, ivs, moms = [], [0], [], []
+    for _ in range(n_regions):
+        ids.append(int(rec[pos]))
+        n = int(rec[pos + 1])
+        ivs.append(rec[pos + 2:pos + 2 + 3 * n].reshape(-1, 3))
+        offs.append(offs[-1] + n)
+        moms.append(rec[pos + 2 + 3 * n:pos + 8 + 3 * n].view(np.float32))
+        pos += 8 + 3 * n
+    d["region_id"] = np.asarray(ids, np.int32)
+    d["interval_offset"] = np.asarray(offs, np.int32)
+    d["intervals"] = np.concatenate(ivs).astype(np.int32) if ivs else np.zeros((0, 3), np.int32)
+    d["shape_moments"] = np.stack(moms) if moms else np.zeros((0, 6), np.float32)
+    levels = []
+    for _ in range(n_levels):
+        nc = int(rec[pos])
+        pos += 1
+        comps = []
+        for _ in range(nc):
+            cid, size, parent, start, end, nn, nch = map(int, rec[pos:pos + 7])
+            pos += 7
+            comps.append(dict(id=cid, size=size, parent_id=parent, start_frame=start, end_frame=end,
+                              neighbors=rec[pos:pos + nn].tolist(), children=rec[pos + nn:pos + nn + nch].tolist()))
+            pos += nn + nch
+        levels.append(comps)
+    d["levels"] = levels
+    if pos != len(rec):
+        raise ValueError("malformed region record")
+    return d
+
+
+class RegionSegmentationUnit:
+    """Mirror of RegionSegmentationUnit: consumes the over-segmentation stream (the dicts a DenseSegmentationUnit
+    returns) together with the video frames (and the flow stream when present), returns hierarchical results."""
+
+    def __init__(self, region_options: Optional[RegionSegmentationOptions] = None, raw_records: bool = False):
+        self.region_options = region_options or RegionSegmentationOptions()
+        self._h = C.c_void_p()
+        self._raw = raw_records
+        self.frame_width = self.frame_height = 0
+        self.input_frames = 0
+
+    def open_streams(self, frame_width: int, frame_height: int, pixel_format: str = PIXEL_FORMAT_BGR24,
+                     flow_stream_present: bool = False) -> bool:
+        if pixel_format != PIXEL_FORMAT_BGR24:
+            log.error("Expecting video format to be BGR24")                    # segmentation_unit.cpp:215-218
+            return False
+        from ._lib import RegionOpts
+        o = RegionOpts()
+        lib().vsb200_region_default_opts(C.byref(o))
+        ro = self.region_options
+        for k in ("min_region_num", "max_region_num", "luminance_bins", "color_bins", "flow_bins", "chunk_set_size",
+                  "chunk_set_overlap", "constraint_chunks"):
+            setattr(o, k, int(getattr(ro, k)))
+        o.level_cutoff_fraction = float(ro.level_cutoff_fraction)
+        o.small_region_penalizer = float(ro.small_region_penalizer)
+        o.save_descriptors = int(ro.save_descriptors)
+        o.use_appearance = int(ro.use_appearance)
+        o.use_flow = int(ro.use_flow and flow_stream_present)                # CreateRegionSegmentation, :303-308
+        o.use_size_penalizer = int(ro.use_size_penalizer)
+        o.compute_vectorization = int(ro.compute_vectorization)
+        rc = lib().vsb200_region_create(C.byref(o), frame_width, frame_height, C.byref(self._h))
+        if rc != 0:
+            log.error("RegionSegmentationUnit: %s", lib().vsb200_last_error().decode(errors="replace"))
+            self._h = C.c_void_p()
+            return False
+        self.frame_width, self.frame_height = frame_width, frame_height
+        self._use_flow = bool(o.use_flow)
+        return True
+
+    def _collect(self, n: int) -> List:
+        out = []
+        for _ in range(n):
+            p = C.POINTER(C.c_int32)()
+            nw = lib().vsb200_region_pop(self._h, C.byref(p))
+            rec = np.ctypeslib.as_array(p, shape=(nw,)).copy()
+            out.append(rec if self._raw else parse_region_record(rec))
+        return out
+
+    def process_frame(self, overseg: dict, bgr: np.ndarray, flow: Optional[np.ndarray] = None) -> List:
+        if not self._h:
+            raise RuntimeError("open_streams() was not called or failed")
+        r, keep = _dict_to_result(overseg)
+        bgr = np.ascontiguousarray(bgr)
+        fl_ptr, fl_stride = None, 0
+        if self._use_flow and self.input_frames > 0:
+            if flow is None:
+                raise ValueError("Flow always has to be passed or be absent.")
+            flow = np.ascontiguousarray(flow, np.float32)
+            fl_ptr, fl_stride = flow.ctypes.data, flow.strides[0]
+        n = C.c_int()
+        check(lib().vsb200_region_push(self._h, C.byref(r), bgr.ctypes.data, bgr.strides[0], fl_ptr, fl_stride, C.byref(n)),
+              "vsb200_region_push")
+        del keep
+        self.input_frames += 1
+        return self._collect(n.value)
+
+    def post_process(self) -> List:
+        n = C.c_int()
+        check(lib().vsb200_region_flush(self._h, C.byref(n)), "vsb200_region_flush")
+        return self._collect(n.value)
+
+    def stats(self) -> dict:
+        a = (C.c_double * 2)()
+        lib().vsb200_region_stats(self._h, a)
+        return dict(kernel_launches=a[0], chunk_sets=a[1])
+
+    def close(self):
+        if self._h:
+            lib().vsb200_region_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
