@@ -154,7 +154,7 @@ int vsb200_bucket_index(float weight);
  * of segmentation_graph.h:158-162,367-374): keys are the 2048 weight buckets, order inside a
  * bucket is (bucket list, anchor pixel, direction).  seg_ptrs[q] = device weights of bucket
  * list q (NULL = absent), q even spatial ([h][w][4]), q odd temporal ([h][w][9]).
- * codes_out: >= total valid edges uint32 edge codes ((q*N + pixel) << 4 | dir);
+ * codes_out: >= total valid edges uint32 edge codes (rank of the edge in (list, pixel, direction) order: (q/2)*13N + (q odd ? 4N : 0) + pixel*nd + dir);
  * bucket_start_out: device uint32/uint64 [2049]. */
 int vsb200_sort_edges(const float* const* host_seg_ptrs, int num_lists, int width, int height,
                       uint32_t* dev_codes_out, uint64_t* dev_bucket_start_out, void* dev_scratch,

@@ -179,6 +179,19 @@ def test_1080p_flow_chunks_match_oracle():
         assert abs(len(g["region_id"]) - nr) <= max(3, nr // 20), (len(g["region_id"]), nr)
 
 
+def test_4k_chunk_matches_oracle():
+    """BASELINE config D geometry (3840x2160, 21 slots allocated: 2.19 G edge codes, beyond the reference's own 32-bit
+    (node, direction) packing): a flushed 6-frame chunk against the oracle."""
+    clip = synth_clip(5, 3840, 2160, 6)
+    got, batches, st = _run_gpu(clip)
+    ref = _run_oracle(clip)
+    ious = _compare(got, ref, exact=False)
+    same = sum(partition_equal(ob.id_map_from_result(r), g["id_map"]) for g, r in zip(got, ref))
+    print("4K min IoU", min(ious), "partition-exact frames", same, "of", len(ref), "merge ms", st["merge_ms"])
+    for g, r in zip(got, ref):
+        assert abs(len(g["region_id"]) - len(r["region_id"])) <= max(2, len(r["region_id"]) // 100)
+
+
 def test_flow_path_matches_oracle():
     pairs = list(synth_flow(21, 160, 120, 24))
     clip = [p[0] for p in pairs]

@@ -121,7 +121,8 @@ def _ref_sorted_codes(lists_np, w, h):
         nd = t.shape[-1]
         idx = np.nonzero(flat >= 0)[0]
         pix, d = idx // nd, idx % nd
-        codes.append(((q * n + pix).astype(np.uint32) << 4) | d.astype(np.uint32))
+        nd = 9 if (q & 1) else 4
+        codes.append(((q // 2) * 13 * n + (4 * n if (q & 1) else 0) + pix * nd + d).astype(np.uint32))
         scale = np.float32(2048) / (np.float32(1.0) + np.float32(1e-6))
         buckets.append(np.minimum(np.float32(2048), flat[idx] * scale).astype(np.int32))
     codes = np.concatenate(codes)

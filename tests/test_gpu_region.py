@@ -141,12 +141,12 @@ def test_dense_and_region_units_chain_end_to_end():
     from video_segment_b200.synth import synth_flow
     from video_segment_b200.unit import (DenseSegmentationOptions, DenseSegmentationUnit, RegionSegmentationOptions,
                                          RegionSegmentationUnit, id_map_from_result)
-    pairs = list(synth_flow(5, 192, 128, 26))
+    pairs = list(synth_flow(5, 192, 128, 34))
     clip = [p[0] for p in pairs]
     flows = [p[1] for p in pairs]
-    dense = DenseSegmentationUnit(dense_seg_options=DenseSegmentationOptions(chunk_size=10), want_id_maps=True)
+    dense = DenseSegmentationUnit(dense_seg_options=DenseSegmentationOptions(chunk_size=8), want_id_maps=True)
     assert dense.open_streams(192, 128, flow_stream_present=True)
-    region = RegionSegmentationUnit(RegionSegmentationOptions(chunk_set_size=2, chunk_set_overlap=1))
+    region = RegionSegmentationUnit(RegionSegmentationOptions(chunk_set_size=3, chunk_set_overlap=1))
     assert region.open_streams(192, 128, flow_stream_present=True)
     out, dense_maps, fed = [], [], [0]
 

@@ -45,6 +45,11 @@ for fl in flags:
     if ref_maps is not None:
         ious = [overseg_iou(a, g["id_map"]) for a, g in zip(ref_maps, got)]
         same = [bool(partition_equal(a, g["id_map"])) for a, g in zip(ref_maps, got)]
+        chunk_ids = [g["chunk_id"] for g in got]
+        per_chunk_iou = {}
+        for c, v in zip(chunk_ids, ious):
+            per_chunk_iou[c] = min(per_chunk_iou.get(c, 1.0), v)
+        rec.update(min_iou_per_chunk=[round(per_chunk_iou[c], 4) for c in sorted(per_chunk_iou)])
         rec.update(min_iou=round(min(ious), 6), exact_frames=int(sum(same)), frames=len(got),
                    first_inexact=(same.index(False) if False in same else -1),
                    regions_gpu=[len(g["region_id"]) for g in got][::6], regions_ref=[len(r["region_id"]) for r in ref][::6])

@@ -34,10 +34,27 @@ __host__ __device__ inline int bucket_of(float w) {
   return (int)(v < 2048.f ? v : 2048.f);
 }
 
-// Edge code: ((list * N + pixel) << 4) | dir.  list = reference bucket-list index
-// (2*slot spatial, 2*slot-1 temporal; dense_segmentation_graph.h:962,1077).
-__host__ __device__ inline uint32_t edge_code(int list, int n_pix, int pixel, int dir) {
-  return (((uint32_t)list * (uint32_t)n_pix + (uint32_t)pixel) << 4) | (uint32_t)dir;
+// Edge code: the edge's rank in (list, pixel, direction) order over ALL lists of the chunk graph, i.e.
+// offset(list) + pixel * nd + dir with nd = 4 (spatial lists, even) / 9 (temporal lists, odd) and
+// offset(list) = (list / 2) * 13 N + (list odd ? 4 N : 0).  list = reference bucket-list index (2*slot spatial,
+// 2*slot-1 temporal; dense_segmentation_graph.h:962,1077).  Dense, so 3840x2160 x 21 slots (2.19 G edges) still
+// fits 32 bits -- the reference's own (node, direction) packing overflows there (dense_segmentation_graph.h:314-324).
+__host__ __device__ inline uint32_t edge_list_offset(int list, uint32_t n_pix) {
+  return (uint32_t)(list >> 1) * 13u * n_pix + ((list & 1) ? 4u * n_pix : 0u);
+}
+__host__ __device__ inline uint32_t edge_code(int list, uint32_t n_pix, uint32_t pixel, uint32_t dir) {
+  return edge_list_offset(list, n_pix) + pixel * ((list & 1) ? 9u : 4u) + dir;
+}
+__host__ __device__ inline void edge_decode(uint32_t code, uint32_t n_pix, int& list, uint32_t& pixel, uint32_t& dir) {
+  const uint32_t pair = code / (13u * n_pix);
+  uint32_t r = code - pair * 13u * n_pix;
+  if (r < 4u * n_pix) { list = (int)(2u * pair); pixel = r >> 2; dir = r & 3u; }
+  else { r -= 4u * n_pix; list = (int)(2u * pair + 1u); pixel = r / 9u; dir = r - pixel * 9u; }
+}
+// largest graph the 32-bit code can address: offset(last list) + its size <= 2^32 - 2 (0xFFFFFFFF marks executed entries)
+__host__ inline bool edge_codes_fit(int num_lists, unsigned long long n_pix) {
+  const unsigned long long total = (unsigned long long)(num_lists / 2) * 13ull * n_pix + ((num_lists & 1) ? 4ull * n_pix : 0ull);
+  return total < 0xFFFFFFFFull;
 }
 
 // ---------------- launch wrappers (host) ----------------

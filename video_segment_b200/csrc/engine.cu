@@ -133,8 +133,8 @@ int vsb200_dense::init() {
   n = w * h;
   max_slots = o.chunk_size + 1;                 // later chunks: virtual + constrained + chunk_size - 1
   const size_t nodes = (size_t)n * max_slots;
-  if ((unsigned long long)(2 * max_slots - 1) * (unsigned long long)n >= (1ull << 28)) {
-    set_error("frame %dx%d x %d slots overflows the 32-bit edge code (SURVEY config D needs 64-bit codes)", w, h, max_slots);
+  if (!edge_codes_fit(2 * max_slots - 1, (unsigned long long)n) || nodes >= (1ull << 31)) {
+    set_error("frame %dx%d x %d slots overflows the 32-bit edge code / node id", w, h, max_slots);
     return VSB200_ERR_UNSUPPORTED;
   }
   // min_region_size: float product truncated (dense_segmentation.cpp:270-272)

@@ -104,10 +104,10 @@ __device__ __forceinline__ void cl_union(int* cl, int a, int b) {
 // edge code -> node ids (region_1 = anchor in the current slot, region_2 = neighbour).
 __device__ __forceinline__ void decode_edge(const MergeParams& p, uint32_t code, int& u, int& v) {
   const int n = p.w * p.h;
-  const uint32_t e = code >> 4;
-  const int dir = (int)(code & 15u);
-  const int list = (int)(e / (uint32_t)n);
-  const int pix = (int)(e - (uint32_t)list * (uint32_t)n);
+  int list;
+  uint32_t upix, udir;
+  edge_decode(code, (uint32_t)n, list, upix, udir);
+  const int pix = (int)upix, dir = (int)udir;
   const int slot = (list + 1) >> 1;
   u = slot * n + pix;
   if ((list & 1) == 0) {   // spatial: R, B, BL, BR
@@ -1100,8 +1100,11 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
             const bool both_con = (acon >= 0 && bcon >= 0);
             // different constraint ids: nothing happens NOW, but a split may reset one of the ids before the scan
             // reaches the edge (segmentation_graph.h:417-437), so the entry stays in the list as dormant (done = 3)
-            dormant = both_con && acon != bcon;
-            drop = dormant || (!both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins);   // inert
+            // (constrained chunks: an inert pair, one side finalised and both big, may still be FORCED together once both
+            // sides carry one constraint id -- it stays dormant as well)
+            const bool inert = !both_con && (af[k] || bf[k]) && asz >= mins && bsz >= mins;
+            dormant = (both_con && acon != bcon) || (inert && p.has_constraints);
+            drop = dormant || inert;
             hubf[k] = !drop && asz >= mins && bsz >= mins;
           }
           p.done[i] = dormant ? 3 : (drop ? 1 : 0);   // done flags of the window are (re)written here
@@ -1389,17 +1392,27 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
               // dormant edge (different constraint ids): a guard of this segment if a split may reach one of its
               // sides -- then the exact paths decide it in order; otherwise it is a certified no-op
               bool guard = false;
+              const int con_y = p.rec[e.y].con, con_z = p.rec[e.z].con;
+              if (con_y >= 0 && con_z >= 0) {
 #pragma unroll
-              for (int s2 = 0; s2 < 2; ++s2) {
-                const int r = s2 ? (int)e.z : (int)e.y;
-                if (p.rec[r].sz >= mins) guard = guard || (p.hull[r].flags & kScSplitCap);
-                else {
-                  const NodeScratch SCg = load_sc(&p.hull[cl_find_compress(p.cl, r)]);
-                  guard = guard || (SCg.flags & kScSplitCap);
-                  if (SCg.hub0 >= 0) guard = guard || (p.hull[SCg.hub0].flags & kScSplitCap);
-                  if (SCg.hub1 >= 0) guard = guard || (p.hull[SCg.hub1].flags & kScSplitCap);
-                  if (SCg.flags & kScHubs3) guard = true;
+                for (int s2 = 0; s2 < 2; ++s2) {
+                  const int r = s2 ? (int)e.z : (int)e.y;
+                  if (p.rec[r].sz >= mins) guard = guard || (p.hull[r].flags & kScSplitCap);
+                  else {
+                    const NodeScratch SCg = load_sc(&p.hull[cl_find_compress(p.cl, r)]);
+                    guard = guard || (SCg.flags & kScSplitCap);
+                    if (SCg.hub0 >= 0) guard = guard || (p.hull[SCg.hub0].flags & kScSplitCap);
+                    if (SCg.hub1 >= 0) guard = guard || (p.hull[SCg.hub1].flags & kScSplitCap);
+                    if (SCg.flags & kScHubs3) guard = true;
+                  }
                 }
+              } else {
+                // inert pair of hubs: a guard if the unconstrained side(s) may take, in this segment, the id that
+                // makes it a same-id pair (what a hub may absorb carries at most one id, or several: unknown)
+                const NodeScratch Hy = load_sc(&p.hull[e.y]), Hz = load_sc(&p.hull[e.z]);
+                const int cand_y = con_y >= 0 ? con_y : ((Hy.flags & kScConMulti) ? -2 : (Hy.con != kNoCon ? Hy.con : -1));
+                const int cand_z = con_z >= 0 ? con_z : ((Hz.flags & kScConMulti) ? -2 : (Hz.con != kNoCon ? Hz.con : -1));
+                guard = (cand_y != -1 && cand_z != -1) && (cand_y == -2 || cand_z == -2 || cand_y == cand_z);
               }
               p.done[e.w] = guard ? 0 : 1;
               continue;
@@ -1636,8 +1649,9 @@ __device__ void run_bucket(const MergeParams& p, Bar& bar, MergeShared& S, const
         if (!drop) {
           const RegionRec A = load_rec(&p.rec[ru]), B = load_rec(&p.rec[rv]);
           const bool both_con = (A.con >= 0 && B.con >= 0);
-          dormant = both_con && A.con != B.con;
-          drop = (!both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins);
+          const bool inert = !both_con && (A.fin || B.fin) && A.sz >= mins && B.sz >= mins;
+          dormant = (both_con && A.con != B.con) || (inert && p.has_constraints);
+          drop = inert && !dormant;
           hubhub = !drop && !dormant && A.sz >= mins && B.sz >= mins;
         }
         if (drop) { p.done[e.w] = 1; continue; }

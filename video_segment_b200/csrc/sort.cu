@@ -9,7 +9,8 @@
 //   pass 2  scan     : exclusive scan in (bucket-major, range-minor) order
 //   pass 3  scatter  : one warp per range walks its elements in order; lanes with equal buckets
 //                      are ranked with __match_any_sync, so the output stays stable
-// Payload = 32-bit edge code ((list * N + pixel) << 4 | dir); the weights themselves are not moved.
+// Payload = 32-bit edge code (rank of the edge in (list, pixel, direction) order, common.cuh); the weights themselves
+// are not moved.
 #include "common.cuh"
 
 namespace vsb {
@@ -23,6 +24,7 @@ struct RangeDesc {
   unsigned start;        // first element of the range inside the list
   unsigned count;        // elements in the range
   unsigned list;         // bucket-list index q
+  unsigned code_base;    // edge code of the list's first element (edge_list_offset)
   unsigned nd;           // 4 (spatial) or 9 (temporal)
 };
 
@@ -162,9 +164,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) scatter_kernel(const Rang
     if (valid) {
       const unsigned rank = __popc(peers & lt_mask);
       if (rank == 0) pos[warp][b] = base + __popc(peers);
-      const unsigned e = rd.start + i;             // element index inside the list: pixel * nd + dir
-      const unsigned pixel = e / rd.nd, dir = e - pixel * rd.nd;
-      codes[base + rank] = ((rd.list * n_pix + pixel) << 4) | dir;
+      codes[base + rank] = rd.code_base + rd.start + i;      // element index inside the list = pixel * nd + dir
     }
     __syncwarp();
   }
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) scatter_kernel(const Rang
 int launch_sort_edges(const float* const* seg_ptrs, int num_lists, int w, int h, uint32_t* codes,
                       unsigned long long* bucket_start, void* scratch, size_t scratch_bytes, cudaStream_t s) {
   const unsigned long long n = (unsigned long long)w * h;
-  if ((unsigned long long)num_lists * n >= (1ull << 28)) {
+  if (!edge_codes_fit(num_lists, n)) {
     set_error("sort_edges: %d lists x %llu pixels overflow the 32-bit edge code", num_lists, n);
     return 5;
   }
@@ -202,6 +202,7 @@ int launch_sort_edges(const float* const* seg_ptrs, int num_lists, int w, int h,
       rd.start = (unsigned)st;
       rd.count = (unsigned)((e - st < kRangeElems) ? (e - st) : kRangeElems);
       rd.list = (unsigned)q;
+      rd.code_base = edge_list_offset(q, (uint32_t)n);
       rd.nd = nd;
       h_tab[k++] = rd;
     }
