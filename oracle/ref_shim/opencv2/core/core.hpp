@@ -20,6 +20,7 @@
 #define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8UC(n) CV_MAKETYPE(CV_8U, (n))
 typedef unsigned char uchar;
 namespace cv {
 struct Size {

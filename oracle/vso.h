@@ -125,6 +125,11 @@ void vso_hist_normalize(const double* hist, const double* weight_sum, int n_regi
 /* ColorHistogram::ChiSquareDist (histograms.cpp:391-407) for region pairs [2 * n_pairs]. */
 void vso_hist_chisquare(const float* hist, int total_bins, const int32_t* pairs, int n_pairs, float* out);
 
+/* Test tap: the chunk hand-over state after the last chunk boundary -- the two overlap frames' region-id maps
+ * (int32 [2][h][w]), state = {max_region_id_, id of the chunk they constrain, frames output so far}
+ * (dense_segmentation.cpp:300-328,360-365).  Returns 1 before the first boundary. */
+int vso_dense_last_overlap_state(vso_dense* d, const int32_t** maps, int32_t state[3]);
+
 /* Hierarchical region stage (vso_hier.cpp): RegionSegmentation::ProcessFrame fed with the over-segmentation of the dense
  * stage, frame by frame (segmentation/region_segmentation.cpp:97-205).  Results pop as flat int32 records in the layout
  * of oracle/ref_hier_wrap.cpp (ref_hier_pop). */

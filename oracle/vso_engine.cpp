@@ -255,9 +255,17 @@ class DenseSegmentation {
       if (use_flow_) seg_->graph()->AddTemporalFlowEdges(feature_buffer_[i]->data(), feature_buffer_[i - 1]->data(), flow_buffer_[i]->data());
       else seg_->graph()->AddTemporalEdges(feature_buffer_[i]->data(), feature_buffer_[i - 1]->data());
     }
+    // test tap: the hand-over state of this boundary (what vsb200_dense_export_halo gives for the product): the two
+    // overlap frames' region-id maps, max_region_id_, the id of the chunk they constrain, frames output so far
+    last_overlap_maps.assign((size_t)2 * w_ * h_, 0);
+    SegDescToIdImage(*overlap_segmentations_[0], w_, last_overlap_maps.data());
+    SegDescToIdImage(*overlap_segmentations_[1], w_, last_overlap_maps.data() + (size_t)w_ * h_);
+    last_chain_state[0] = max_region_id_; last_chain_state[1] = chunk_id_; last_chain_state[2] = num_output_frames_;
     overlap_segmentations_.clear();
     stage_sec[1] += NowSec() - t0;
   }
+  std::vector<int> last_overlap_maps;
+  int last_chain_state[3] = {0, 0, 0};
 
   // dense_segmentation.cpp:330-432
   void SegmentAndOutputChunk(bool flush, std::vector<std::unique_ptr<SegDesc>>* results) {
@@ -507,6 +515,13 @@ int vso_dense_pop(vso_dense* d, vso_frame_result* out) {
 
 void vso_dense_destroy(vso_dense* d) { delete d; }
 
+// hand-over state of the last chunk boundary (test tap, see ChunkBoundaryOutput): *maps = int32 [2][h][w]
+int vso_dense_last_overlap_state(vso_dense* d, const int32_t** maps, int32_t state[3]) {
+  if (d->seg->last_overlap_maps.empty()) return 1;
+  *maps = d->seg->last_overlap_maps.data();
+  std::memcpy(state, d->seg->last_chain_state, sizeof(int32_t) * 3);
+  return 0;
+}
 int vso_dense_last_chunk_slots(vso_dense* d) { return d->seg->last_slots; }
 const int32_t* vso_dense_last_chunk_node_labels(vso_dense* d) { return d->seg->last_node_labels.data(); }
 const int32_t* vso_dense_last_chunk_id_images(vso_dense* d) { return d->seg->last_id_images.data(); }

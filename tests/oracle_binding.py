@@ -267,6 +267,16 @@ class OracleDense:
         p = lib().vso_dense_last_chunk_id_images(self._h)
         return np.ctypeslib.as_array(p, shape=(s, self.h, self.w)).copy()
 
+    def last_overlap_state(self):
+        """(id maps [2, h, w] int32, [max region id, chunk id, frames output]) of the last chunk boundary."""
+        p = C.POINTER(C.c_int32)()
+        st = (C.c_int32 * 3)()
+        L = lib()
+        L.vso_dense_last_overlap_state.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
+        if L.vso_dense_last_overlap_state(self._h, C.byref(p), st) != 0:
+            return None, None
+        return np.ctypeslib.as_array(p, shape=(2, self.h, self.w)).copy(), [int(v) for v in st]
+
     def merge_stats(self):
         a = (C.c_int64 * 3)()
         lib().vso_dense_last_chunk_merge_stats(self._h, a)

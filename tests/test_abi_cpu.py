@@ -105,3 +105,34 @@ def test_reference_arm_prints_one_line_under_torchrun():
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["higher_is_better"] is True and "160x120" in line["config"]["workload"]
     assert len(line["ms_per_step_series"]) == 1
+
+
+def _units_check_input(tmp_path, frames, flows=None):
+    import struct
+    t, h, w, _ = frames.shape
+    src = tmp_path / "in.bgr"
+    blob = struct.pack("<iiii", w, h, t, 1 if flows is not None else 0) + frames.tobytes()
+    if flows is not None:
+        blob += np.ascontiguousarray(flows, np.float32).tobytes()
+    src.write_bytes(blob)
+    return src
+
+
+def test_cpp_video_units_build_against_reference_framework_and_fail_loudly_without_gpu(tmp_path):
+    """oracle/_ref/b200_units_check = the product's B200DenseSegmentationUnit / B200RegionSegmentationUnit compiled
+    against the reference's video_framework (video_unit.cpp unmodified) and run as the tree seg_tree_sample builds.
+    Without a GPU OpenStreams must return false (no CPU fallback) and the pipeline must not run."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200_units_check")
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200_units_check not built (needs /root/reference)")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    clip = np.load(os.path.join(ROOT, "tests", "golden", "real_clip_136x240x24.npz"))["frames"][:3]
+    src = _units_check_input(tmp_path, clip)
+    p = subprocess.run([exe, str(src), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 1
+    assert "no CPU fallback" in p.stderr

@@ -150,18 +150,62 @@ def test_1080p_constrained_chunks_match_oracle():
 
 
 def test_config_b_300_frames_tracks_oracle():
-    """BASELINE config B for real: 640x480 x 300 synthetic frames = 16 chunks, every frame against the oracle.
-    Settles whether the region count grows chunk over chunk in the product only (profiles/r01_merge_constant_sweeps):
-    the per-chunk trajectory of the product must track the oracle's."""
+    """BASELINE config B for real: 640x480 x 300 synthetic frames = 16 chunks, every frame against the oracle, two ways.
+    (1) Chunk by chunk: every constrained chunk is started from the ORACLE's hand-over state (its two overlap id maps,
+        region-id counter, chunk and frame counters through vsb200_dense_import_halo) and compared with the oracle's
+        chunk: IoU >= 0.99 on every frame of all 15 constrained chunks -- the parity of the chunk computation itself.
+    (2) As one chain: both chains feed on their own results, so a deviation in chunk k changes the constraints of every
+        later chunk and the comparison compounds; the per-chunk region-count trajectory must track the oracle's within
+        max(3, 2 %) and the IoU stays >= 0.99 through the first four chunks and >= 0.96 through all sixteen (reported)."""
+    import torch
+    from video_segment_b200.unit import DenseSegmentationUnit
     clip = synth_clip(7, 640, 480, 300)
+    # the oracle chain, with its hand-over state after every boundary
+    o = ob.OracleDense(640, 480, num_threads=8)
+    ref, handover = [], []
+    for f in clip:
+        r = o.push(f)
+        if r:
+            maps, state = o.last_overlap_state()
+            handover.append((len(ref) + len(r), maps, state))
+        ref += r
+    ref += o.flush()
+    o.close()
+    assert len(handover) == 15 and [h[2][1] for h in handover] == list(range(1, 16))
+    # (1) chunk by chunk
+    per_chunk = []
+    for out_so_far, maps, state in handover:
+        assert state[2] == out_so_far
+        u = DenseSegmentationUnit(want_id_maps=True)
+        assert u.open_streams(640, 480)
+        halo = torch.from_numpy(maps).cuda()
+        u.import_halo(halo[0].data_ptr(), halo[1].data_ptr(), state)
+        got = []
+        k = out_so_far                       # the frame of the second map: the predecessor's last pushed frame
+        while not got and k < len(clip):
+            got += u.process_frame(clip[k], pts=k)
+            k += 1
+        if not got:
+            got += u.post_process()
+        u.close()
+        want = ref[out_so_far:out_so_far + len(got)]
+        ious = [overseg_iou(ob.id_map_from_result(r), g["id_map"]) for g, r in zip(got, want)]
+        assert [g["chunk_id"] for g in got] == [r["chunk_id"] for r in want]
+        per_chunk.append(min(ious))
+    print("config B chunk by chunk from the oracle's state: min IoU per chunk", [round(x, 4) for x in per_chunk])
+    assert min(per_chunk) >= 0.99, per_chunk
+    # (2) one chain
     got, batches, st = _run_gpu(clip)
-    ref = _run_oracle(clip)
-    ious = _compare(got, ref, exact=False)
+    ious = _compare(got, ref, min_iou=0.96, exact=False)
     tg, tr = _chunk_trajectory(got), _chunk_trajectory(ref)
-    print("config B: min IoU", min(ious), "mean", float(np.mean(ious)), "trajectory gpu", tg, "ref", tr)
+    chain = {}
+    for g, v in zip(got, ious):
+        chain[g["chunk_id"]] = min(chain.get(g["chunk_id"], 1.0), v)
+    print("config B as one chain: min IoU per chunk", [round(chain[c], 4) for c in sorted(chain)], "trajectory gpu", tg, "ref", tr)
     assert len(tg) == len(tr) == 16
+    assert min(chain[c] for c in range(4)) >= 0.99
     for (cg, ng), (cr, nr) in zip(tg, tr):
-        assert cg == cr and abs(ng - nr) <= max(3, nr // 20), (cg, ng, nr)
+        assert cg == cr and abs(ng - nr) <= max(3, nr // 50), (cg, ng, nr)
 
 
 def test_1080p_flow_chunks_match_oracle():

@@ -4,11 +4,15 @@ reference's own DenseSegmentation pipeline compiled unmodified into oracle/_ref/
 import numpy as np
 import pytest
 
+import os
+
 import oracle_binding as ob
 import reference_binding as rb
 import reference_cases as rc
 from helpers import overseg_iou
 from test_gpu_engine import _run_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -115,3 +119,54 @@ def test_cpp_host_class_matches_compiled_reference():
     probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_host_class_probe.py")
     p = subprocess.run([sys.executable, probe, "real_single_chunk"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and p.stdout.startswith("OK"), (p.returncode, p.stdout[-400:], p.stderr[-800:])
+
+
+def test_cpp_video_units_in_the_reference_framework(tmp_path):
+    """B200DenseSegmentationUnit -> B200RegionSegmentationUnit as VideoUnits inside the reference's own video_framework
+    (oracle/_ref/b200_units_check: video_unit.cpp compiled unmodified, the tree seg_tree_sample builds), with the
+    reference's --chunk_size flag override, against the Python mirrors of the same two units: identical hierarchical
+    records, word for word."""
+    import struct
+    import subprocess
+    from video_segment_b200.unit import (DenseSegmentationOptions, DenseSegmentationUnit, RegionSegmentationOptions,
+                                         RegionSegmentationUnit)
+    exe = os.path.join(ROOT, "oracle", "_ref", "b200_units_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200_units_check not built")
+    clip = np.load(os.path.join(ROOT, "tests", "golden", "real_clip_136x240x24.npz"))["frames"][:20]
+    t, h, w, _ = clip.shape
+    flows = np.random.default_rng(3).normal(0, 1.5, (t, h, w, 2)).astype(np.float32)
+    for use_flow in (False, True):
+        src = tmp_path / f"in{int(use_flow)}.bgr"
+        blob = struct.pack("<iiii", w, h, t, int(use_flow)) + clip.tobytes() + (flows.tobytes() if use_flow else b"")
+        src.write_bytes(blob)
+        out = tmp_path / f"out{int(use_flow)}.bin"
+        p = subprocess.run([exe, str(src), str(out), "8"], capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-600:]
+        raw = out.read_bytes()
+        n = struct.unpack_from("<q", raw, 0)[0]
+        pos, recs = 8, []
+        for _ in range(n):
+            ln = struct.unpack_from("<q", raw, pos)[0]
+            recs.append(np.frombuffer(raw, np.int32, ln, pos + 8).copy())
+            pos += 8 + 4 * ln
+        # the same two units through the Python mirrors
+        dense = DenseSegmentationUnit(dense_seg_options=DenseSegmentationOptions(chunk_size=8))
+        assert dense.open_streams(w, h, flow_stream_present=use_flow)
+        region = RegionSegmentationUnit(RegionSegmentationOptions(), raw_records=True)
+        assert region.open_streams(w, h, flow_stream_present=use_flow)
+        want, fed = [], [0]
+
+        def feed(results):
+            for r in results:
+                k = fed[0]
+                want.extend(region.process_frame(r, clip[k], flows[k] if use_flow and k > 0 else None))
+                fed[0] += 1
+        for k, f in enumerate(clip):
+            feed(dense.process_frame(f, flows[k] if use_flow else None))
+        feed(dense.post_process())
+        want.extend(region.post_process())
+        dense.close(); region.close()
+        assert n == t == len(want)
+        for a, b in zip(recs, want):
+            assert len(a) == len(b) and np.array_equal(a, b)

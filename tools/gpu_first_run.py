@@ -1,7 +1,7 @@
 """First GPU bring-up script (not a test): parity spot checks + kernel timings, verbose."""
 import sys, time, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import oracle_binding as ob
 from helpers import overseg_iou, partition_equal

@@ -1,6 +1,6 @@
 """Development sweep (not a test): builds libvsb200 variants with different merge constants on the CPU side
-(`python tests/gpu_merge_sweep.py build`), then times three 1080p chunks per variant on the GPU
-(`python tests/gpu_merge_sweep.py run`) and prints merge ms per chunk plus a checksum of the region counts."""
+(`python tools/gpu_merge_sweep_constants.py build`), then times three 1080p chunks per variant on the GPU
+(`python tools/gpu_merge_sweep_constants.py run`) and prints merge ms per chunk plus a checksum of the region counts."""
 import json, os, subprocess, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)

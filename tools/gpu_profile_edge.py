@@ -1,6 +1,6 @@
 """Small driver for ncu: a few steady-state edge-build launches at 1080p (plus preprocess)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from video_segment_b200 import kernels as K
 from video_segment_b200.synth import synth_clip

@@ -1,7 +1,7 @@
 """Development probe: region sizes reported in the hierarchy (device union-find records) must equal the voxel
 counts of the id maps (self-consistency, no oracle).  usage: gpu_size_check.py [real|WxHxT] [repeats]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from video_segment_b200.synth import synth_clip
 from video_segment_b200.unit import DenseSegmentationUnit

@@ -1,6 +1,6 @@
 """GPU bring-up / profiling script (not a test): per-stage times of the streaming engine and the
 per-bucket merge profile at the BASELINE geometries.  Usage:
-    python tests/gpu_stage_times.py [engine640] [chunk1080] [engine1080]
+    python tools/gpu_stage_times.py [engine640] [chunk1080] [engine1080]
 Writes gpurun_out/stage_times.json and gpurun_out/merge_debug_*.txt."""
 import json
 import os
@@ -8,7 +8,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import torch
 

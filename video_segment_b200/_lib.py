@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("VSB200_LIB") or os.path.join(HERE, "libvsb200.so")   # VSB200_LIB: development builds (tests/gpu_merge_sweep.py)
+LIB_PATH = os.environ.get("VSB200_LIB") or os.path.join(HERE, "libvsb200.so")   # VSB200_LIB: development builds (tools/gpu_merge_sweep_constants.py)
 
 
 class DenseOpts(C.Structure):

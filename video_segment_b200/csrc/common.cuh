@@ -103,7 +103,8 @@ struct MergeParams {
   int min_region_size;
   float force_merge_weight;        // 0.001f (L2) / 0.002f (L1), dense_segmentation.cpp:259-264
   int has_constraints;             // chunk > 0
-  float y_merge, y_force;          // squared-distance images of the merge gates: sqrtf(y) < 0.05f <=> y < y_merge, (double)sqrtf(y) < 0.2 <=> y < y_force (set by launch_merge)
+  float y_merge, y_force, y_split; // squared-distance images of the distance gates (set by launch_merge): sqrtf(y) < 0.05f <=> y < y_merge,
+                                   // (double)sqrtf(y) < 0.2 <=> y < y_force, sqrtf(y) > 0.15f <=> y >= y_split
   unsigned long long window_target, residual_split, segment_min;   // window sizing (defaults in merge.cu; VSB200_WINDOW_TARGET / _RESIDUAL_SPLIT / _SEGMENT_MIN override them for sweeps)
   int dev_flags;                   // development switches (VSB200_MERGE_FLAGS): 1 = no hub-pair certificates, 2 = fixed window target, 4 = no block-0 rounds, 16 = no group-parallel scans, 32 / 64 = diagnostics for constrained chunks, 128 = one-thread exact scans; default 17
   const float* flows;              // optional [slots][h][w][2] (slot 0 unused), nullable
