@@ -19,8 +19,8 @@ n += len(u.post_process())
 u.close()
 print("dense frames", n)
 if os.environ.get("PROFILE_REGION", "1") == "1":
-    pairs = list(synth_flow(5, 640, 360, 14))
-    d = DenseSegmentationUnit(dense_seg_options=DenseSegmentationOptions(chunk_size=6))
+    pairs = list(synth_flow(5, 640, 360, 30))
+    d = DenseSegmentationUnit(dense_seg_options=DenseSegmentationOptions(chunk_size=8))
     assert d.open_streams(640, 360, flow_stream_present=True)
     r = RegionSegmentationUnit(RegionSegmentationOptions(chunk_set_size=3, chunk_set_overlap=1), raw_records=True)
     assert r.open_streams(640, 360, flow_stream_present=True)
