@@ -458,6 +458,7 @@ struct ScanShared {
   int2 rec[2 * kScanMax][3];                        // 24-byte records (sz, con | d0, d1 | d2, fin): three 64-bit shared accesses each
   unsigned hkey[4 * kScanMax];                      // hash: global root + 1 (0 = empty)
   unsigned short hidx[4 * kScanMax];                // local id of the slot's root
+  int n_snap, spec_fail;                            // split scan: speculated conditional meetings (snapshots used, a prediction failed)
   int n_roots;
   int hbits;                                        // hash size of the current scan: 4 x its edge count, rounded up to a power of two
 };
@@ -647,13 +648,24 @@ __device__ void exact_scan(const MergeParams& p, ScanShared& C, const int b, con
 //     events only: one thread replays the events in reference order (absorb: ~100 cycles with the
 //     hub's record in registers and the gates taken on the squared distance; big-big: the generic
 //     decision tree).
-//   * the one conditional case, a constrained piece meeting a hub (same id: merge only within 0.15;
-//     other id: nothing), suspends its sub-cluster at that edge: the rest of the sub-cluster's edges
-//     are flagged generic and decided by the event thread in order, with the full decision tree.
+//   * the one conditional case is a CONSTRAINED piece meeting a hub (same id: merge only within 0.15;
+//     other id: nothing; unconstrained hub: it takes the id).  The replay thread predicts the outcome
+//     from the hub's staged record -- decisive cases only: different ids, an unconstrained hub, or a
+//     same-id distance more than 0.02 away from the gate -- keeps a snapshot of the piece and goes on;
+//     the event thread re-decides the meeting with the hub's actual record and, if the piece's side of
+//     the outcome differs from the prediction, the whole scan is redone by the one-thread walk
+//     (nothing has been written back yet).  Non-decisive meetings, or more than 256 of them, suspend
+//     the sub-cluster: the rest of its edges are decided by the event thread, in order.
 // Same decisions, same float operations per merge as the one-thread walk; only independent work is
 // reordered.
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned kEvNone = 0, kEvAbsorb = 1, kEvBB = 2;
+constexpr unsigned kEvNone = 0, kEvAbsorb = 1, kEvBB = 2, kEvCond = 3;
+constexpr int kSnapMax = 256;          // speculated conditional meetings per scan (two 4 KB banks of 32-byte snapshots)
+struct __align__(16) CondSnap {        // the piece's record when it met the hub, and what the replay thread assumed
+  int2 r0, r1, r2;                     // (sz, con) (d0, d1) (d2, fin)
+  int piece;
+  int flags;                           // 1: the hub is on the region_1 side, 2: assumed merged, 4: assumed the piece's id reset
+};
 __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, const uint32_t* codes, const uint32_t* pend_list,
                            const int n_pend, unsigned char* done_flags) {
   ScanShared& C = S.scan;
@@ -674,11 +686,14 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
   int* const sc = reinterpret_cast<int*>(C.hkey);         // [2 kScanMax] sub-cluster union-find over the small roots
   unsigned* const keys = C.hkey + 2 * kScanMax;           // [kScanMax] (sub-cluster << 11 | edge index), sorted
   unsigned short* const elist = reinterpret_cast<unsigned short*>(C.hkey + 3 * kScanMax);   // [kScanMax] edges the event thread looks at
+  CondSnap* const snap_a = reinterpret_cast<CondSnap*>(C.hkey + 3 * kScanMax + kScanMax / 2);     // [128] (last 4 KB of hkey)
+  CondSnap* const snap_b = reinterpret_cast<CondSnap*>(reinterpret_cast<unsigned char*>(C.tru) + 2 * kScanMax);   // [128] (upper half of tru)
+  auto snap_at = [&](int k) -> CondSnap* { return k < kSnapMax / 2 ? snap_a + k : snap_b + (k - kSnapMax / 2); };
   // ---- staging: current roots of the edges -> compact local ids, records into shared memory ----
   int hbits = 6;
   while ((1 << hbits) < 4 * n_pend) ++hbits;
   for (int i = tid; i < (1 << hbits); i += nthr) { C.hkey[i] = 0u; C.hidx[i] = 0xFFFFu; }
-  if (tid == 0) { C.n_roots = 0; C.hbits = hbits; }
+  if (tid == 0) { C.n_roots = 0; C.hbits = hbits; C.n_snap = 0; C.spec_fail = 0; }
   __syncthreads();
   for (int i = tid; i < n_pend; i += nthr) {
     const uint32_t pos = pend_list[i];
@@ -760,7 +775,34 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
       if (ha >= 0 || hb >= 0) {
         const int h = ha >= 0 ? ha : hb, x = ha >= 0 ? rb : ra;
         if (C.rec[x][0].y >= 0) {
-          // a constrained piece meets a hub: conditional on the hub's record -> the event thread takes over from here
+          // a constrained piece meets a hub: conditional on the hub's record.  Decisive cases are predicted from the hub's
+          // staged record and verified by the event thread; the others suspend the sub-cluster.
+          const bool hub_is_a = ha >= 0;
+          RegionRec H0 = scan_load(C.rec, h), Xc = scan_load(C.rec, x);
+          const RegionRec Xb = Xc;
+          bool decisive = true;
+          if (H0.con >= 0 && H0.con == Xb.con) {
+            const float dist = raw_dist(H0, Xb);
+            const float gate = force_bucket ? 0.2f : 0.15f;
+            decisive = fabsf(dist - gate) > 0.02f;
+          }
+          int k = kSnapMax;
+          if (decisive) k = atomicAdd(&C.n_snap, 1);
+          if (k < kSnapMax) {
+            const int r = hub_is_a ? decide_pair(p, H0, Xc, edge_w) : decide_pair(p, Xc, H0, edge_w);
+            const bool merged = r != 0;
+            const bool reset = !merged && Xc.con != Xb.con;
+            CondSnap* sn = snap_at(k);
+            sn->r0 = make_int2(Xb.sz, Xb.con);
+            sn->r1 = make_int2(__float_as_int(Xb.d0), __float_as_int(Xb.d1));
+            sn->r2 = make_int2(__float_as_int(Xb.d2), Xb.fin);
+            sn->piece = x;
+            sn->flags = (hub_is_a ? 1 : 0) | (merged ? 2 : 0) | (reset ? 4 : 0);
+            ev_a[i] = (unsigned short)h; ev_b[i] = (unsigned short)k; evt[i] = kEvCond;
+            if (merged) owner[x] = (unsigned short)h;
+            else if (reset) C.rec[x][0].y = Xc.con;
+            continue;
+          }
           for (int q2 = q; q2 < n_pend; ++q2) {
             const unsigned k2 = keys[q2];
             if ((k2 >> 11) != (k0 >> 11)) break;
@@ -813,7 +855,8 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
         if (gen[my_i]) { my_kind = 2; my_a = C.ea[my_i]; my_b = C.eb[my_i]; }
         else {
           my_a = ev_a[my_i]; my_b = ev_b[my_i];
-          if (evt[my_i] == kEvAbsorb) {
+          if (evt[my_i] == kEvCond) my_kind = 3;
+          else if (evt[my_i] == kEvAbsorb) {
             const int2 x0 = C.rec[my_b][0], x1 = C.rec[my_b][1], x2 = C.rec[my_b][2];      // (sz, con) (d0, d1) (d2, fin); con < 0
             my_sz = x0.x; my_fin = x2.y;
             my_d0 = __int_as_float(x1.x); my_d1 = __int_as_float(x1.y); my_d2 = __int_as_float(x2.x);
@@ -851,8 +894,30 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
           ++n_abs;
           continue;
         }
-        // big-big / generic: lane 0 with the full decision tree, on the records in shared memory
+        // big-big / generic / speculated meetings: lane 0 with the full decision tree, on the records in shared memory
         if (cur >= 0) { if (lane == 0) scan_store(C.rec, cur, H); cur = -1; }
+        if (kind == 3) {
+          int fail = 0;
+          if (lane == 0) {
+            const CondSnap sn = *snap_at(eb_);
+            const int h = findl(ea_);
+            RegionRec Hh = scan_load(C.rec, h), X;
+            X.sz = sn.r0.x; X.con = sn.r0.y; X.d0 = __int_as_float(sn.r1.x); X.d1 = __int_as_float(sn.r1.y); X.d2 = __int_as_float(sn.r2.x);
+            X.fin = sn.r2.y; X.pad0 = X.pad1 = 0;
+            const int xcon0 = X.con;
+            const int r = (sn.flags & 1) ? decide_pair(p, Hh, X, edge_w) : decide_pair(p, X, Hh, edge_w);
+            const bool merged = r != 0, reset = !merged && X.con != xcon0;
+            if (merged != ((sn.flags & 2) != 0) || reset != ((sn.flags & 4) != 0)) { fail = 1; C.spec_fail = 1; }
+            else {
+              scan_store(C.rec, h, Hh);
+              if (merged) C.par[sn.piece] = (unsigned short)h;
+            }
+          }
+          fail = __shfl_sync(0xffffffffu, fail, 0);
+          ++n_gen;
+          if (fail) { e0 = n_ev; break; }
+          continue;
+        }
         if (lane == 0) {
           const int a = findl(ea_), bq = findl(eb_);
           if (a != bq) {
@@ -880,6 +945,14 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
     }
   }
   __syncthreads();
+  if (C.spec_fail) {
+    // a predicted meeting came out differently with the hub's actual record: nothing has been written back, the
+    // one-thread walk redoes the list from global memory
+    if (p.debug && tid == 0) atomicAdd(&p.debug[kNumBuckets * 4 + 62], 1ull);
+    __syncthreads();
+    exact_scan(p, C, b, codes, pend_list, n_pend, done_flags, -1, nullptr, nullptr);
+    return;
+  }
   for (int j = tid; j < n_roots; j += nthr) {
     int x = j;
     while (C.par[x] != x) x = C.par[x];
@@ -890,6 +963,7 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
   for (int i = tid; i < n_pend; i += nthr) done_flags[C.epos[i]] = 1;
   if (tid == 0) atomicAdd(&p.stats[3], 1ull);
   __syncthreads();
+  if (p.debug && tid == 0) atomicAdd(&p.debug[kNumBuckets * 4 + 61], (unsigned long long)min(C.n_snap, kSnapMax));
   if (p.debug && tid == 0) {      // development tap: cycles per stage
     atomicAdd(&p.debug[kNumBuckets * 4 + 50], (unsigned long long)(t3 - t2));       // event thread
     atomicAdd(&p.debug[kNumBuckets * 4 + 51], (unsigned long long)(clock64() - t0));  // whole scan
