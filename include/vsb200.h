@@ -166,6 +166,17 @@ size_t vsb200_sort_scratch_bytes(int num_lists, int width, int height);
 int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slots, int l1,
                          int min_region_size, int32_t* dev_labels_out, double* stats4, void* stream);
 
+/* K11 + K10 (csrc/shape.cu): N4 connected components of every label in every frame of a label volume and their shape
+ * moments -- ConnectedComponents(raster, N4_CONNECT) (segment_util/segmentation_util.cpp:1007-1101) and
+ * ShapeMomentsFromRasterization (:652-693) for all regions of all frames at once, as
+ * DenseSegmentationGraph::EnforceSpatialConnectedness (dense_segmentation_graph.h:666-777) needs them.
+ * dev_labels [slices][h][w].  Components are numbered in the order of their first scan interval over the volume.
+ * dev_component_out (may be NULL) [slices][h][w]: component number of every pixel.  host_records_out (may be NULL): up
+ * to record_cap records of 10 words: first interval, #intervals, label, slice, area (int32), mean_x, mean_y, xx, xy, yy
+ * (float bits).  *n_components_out = number of components. */
+int vsb200_label_components(const int32_t* dev_labels, int width, int height, int slices, int32_t* dev_component_out,
+                            int32_t* host_records_out, int record_cap, int* n_components_out, void* stream);
+
 /* ---- region stage, appearance descriptor (csrc/region_hist.cu) ---- */
 
 /* cv::cvtColor(CV_BGR2Lab) on 8-bit data, AppearanceExtractor (segmentation/region_descriptor.cpp:59-89, :73).

@@ -1,8 +1,10 @@
-// TEST INFRASTRUCTURE ONLY.  The product's host-side region bookkeeping (video_segment_b200/csrc/host_shape.hpp: the
-// O(#scan intervals) helpers the streaming engine runs on the host) against the REFERENCE's own functions of
+// TEST INFRASTRUCTURE ONLY.  The product's host-side shape arithmetic (video_segment_b200/csrc/shape_math.hpp: the
+// moment accumulator the device kernel of shape.cu and the host share, shape descriptors, oriented boxes;
+// csrc/region_raster.hpp: raster union of the hierarchical stage) against the REFERENCE's own functions of
 // segment_util/segmentation_util.cpp (compiled unmodified in oracle/_ref/libref_results.so) on random rasters:
-// ShapeMomentsFromRasterization, GetShapeDescriptorFromShapeMoment, MergeRasterization, ConnectedComponents (N4),
-// RasterizationArea, ShapeDescriptorBox / ShapeDescriptorBoxesIntersect.  Floats are compared by bits.  CPU test.
+// ShapeMomentsFromRasterization, GetShapeDescriptorFromShapeMoment, MergeRasterization, RasterizationArea,
+// ShapeDescriptorBox / ShapeDescriptorBoxesIntersect.  Floats are compared by bits.  CPU test.  (Connected components
+// and the per-region moments of the dense engine run on the device: tests/test_gpu_kernels.py.)
 #include <stdint.h>
 #include <string.h>
 
@@ -14,7 +16,8 @@
 
 #include "segment_util/segmentation_util.h"
 
-#include "../video_segment_b200/csrc/host_shape.hpp"
+#include "../video_segment_b200/csrc/region_raster.hpp"
+#include "../video_segment_b200/csrc/shape_math.hpp"
 
 namespace {
 
@@ -43,7 +46,7 @@ void RandomRaster(std::mt19937& rng, int w, int h, std::vector<uint8_t>* mask, s
 }
 
 void ToRasters(const std::vector<uint8_t>& mask, const std::vector<uint8_t>& colour, int part, int w, int h,
-               vsbh::Raster* mine, Rasterization* ref) {
+               vsbr::Raster* mine, Rasterization* ref) {
   mine->clear();
   ref->Clear();
   for (int y = 0; y < h; ++y) {
@@ -63,7 +66,7 @@ void ToRasters(const std::vector<uint8_t>& mask, const std::vector<uint8_t>& col
   }
 }
 
-bool SameRaster(const vsbh::Raster& a, const Rasterization& b) {
+bool SameRaster(const vsbr::Raster& a, const Rasterization& b) {
   if ((int)a.size() != b.scan_inter_size()) return false;
   for (int i = 0; i < (int)a.size(); ++i)
     if (a[i].y != b.scan_inter(i).y() || a[i].lx != b.scan_inter(i).left_x() || a[i].rx != b.scan_inter(i).right_x()) return false;
@@ -80,29 +83,29 @@ extern "C" int host_shape_check(unsigned seed, int n_cases, char* msg, int msg_c
     if (first.empty()) first = "case " + std::to_string(c) + ": " + what;
     ++bad;
   };
-  std::vector<vsbh::Shape> shapes_mine;
+  std::vector<vsbs::Shape> shapes_mine;
   std::vector<segmentation::ShapeDescriptor> shapes_ref;
   for (int c = 0; c < n_cases; ++c) {
     const int w = 8 + rng() % 56, h = 8 + rng() % 40;
     std::vector<uint8_t> mask, colour;
     RandomRaster(rng, w, h, &mask, &colour);
-    vsbh::Raster all, p0, p1;
+    vsbr::Raster all, p0, p1;
     Rasterization rall, r0, r1;
     ToRasters(mask, colour, -1, w, h, &all, &rall);
     ToRasters(mask, colour, 0, w, h, &p0, &r0);
     ToRasters(mask, colour, 1, w, h, &p1, &r1);
     if (all.empty()) continue;
-    if (vsbh::raster_area(all) != segmentation::RasterizationArea(rall)) fail(c, "raster_area");
+    if (vsbr::raster_area(all) != segmentation::RasterizationArea(rall)) fail(c, "raster_area");
     // moments + shape descriptor
     segmentation::ShapeMoments rm;
     segmentation::ShapeMomentsFromRasterization(rall, &rm);
-    const vsbh::Moments mm = vsbh::moments_of(all);
-    if (!SameBits(mm.size, rm.size()) || !SameBits(mm.mx, rm.mean_x()) || !SameBits(mm.my, rm.mean_y()) ||
+    const vsbs::Moments mm = vsbr::moments_of(all);
+    if (!SameBits(mm.size, rm.size()) || !SameBits(mm.mean_x, rm.mean_x()) || !SameBits(mm.mean_y, rm.mean_y()) ||
         !SameBits(mm.xx, rm.moment_xx()) || !SameBits(mm.xy, rm.moment_xy()) || !SameBits(mm.yy, rm.moment_yy()))
       fail(c, "moments_of");
     segmentation::ShapeDescriptor rs;
     segmentation::GetShapeDescriptorFromShapeMoment(rm, &rs);
-    const vsbh::Shape ms = vsbh::shape_of(mm);
+    const vsbs::Shape ms = vsbs::shape_from_moments(mm);
     if (!SameBits(ms.center.x, rs.center.x) || !SameBits(ms.center.y, rs.center.y) || !SameBits(ms.mag_major, rs.mag_major) ||
         !SameBits(ms.mag_minor, rs.mag_minor) || !SameBits(ms.dir_major.x, rs.dir_major.x) || !SameBits(ms.dir_major.y, rs.dir_major.y) ||
         !SameBits(ms.dir_minor.x, rs.dir_minor.x) || !SameBits(ms.dir_minor.y, rs.dir_minor.y))
@@ -111,36 +114,25 @@ extern "C" int host_shape_check(unsigned seed, int n_cases, char* msg, int msg_c
     shapes_ref.push_back(rs);
     // merging the two disjoint halves gives back the whole, interval for interval like the reference
     if (!p0.empty() && !p1.empty()) {
-      vsbh::Raster merged;
-      vsbh::merge_rasters(p0, p1, &merged);
+      vsbr::Raster merged;
+      vsbr::merge_rasters(p0, p1, &merged);
       Rasterization rmerged;
       segmentation::MergeRasterization(r0, r1, &rmerged);
       if (!SameRaster(merged, rmerged)) fail(c, "merge_rasters");
-    }
-    // N4 connected components, same components in the same order
-    std::vector<vsbh::Raster> comps;
-    std::vector<Rasterization> rcomps;
-    const int n_mine = vsbh::components_n4(all, &comps);
-    const int n_ref = segmentation::ConnectedComponents(rall, segmentation::N4_CONNECT, &rcomps);
-    if (n_mine != n_ref || comps.size() != rcomps.size()) {
-      fail(c, "components_n4 count");
-    } else {
-      for (size_t k = 0; k < comps.size(); ++k)
-        if (!SameRaster(comps[k], rcomps[k])) { fail(c, "components_n4 raster"); break; }
     }
   }
   // oriented boxes of consecutive shapes: corners and the intersection verdict
   for (size_t k = 0; k + 1 < shapes_mine.size(); ++k) {
     for (float border : {0.0f, 2.0f}) {
-      vsbh::Vec2 a[4], b[4];
-      vsbh::shape_box(shapes_mine[k], border, a);
-      vsbh::shape_box(shapes_mine[k + 1], border, b);
+      vsbs::Vec2 a[4], b[4];
+      vsbs::shape_box(shapes_mine[k], border, a);
+      vsbs::shape_box(shapes_mine[k + 1], border, b);
       std::vector<cv::Point2f> ra, rb;
       segmentation::ShapeDescriptorBox(shapes_ref[k], border, &ra);
       segmentation::ShapeDescriptorBox(shapes_ref[k + 1], border, &rb);
       for (int i = 0; i < 4; ++i)
         if (!SameBits(a[i].x, ra[i].x) || !SameBits(a[i].y, ra[i].y)) { fail((int)k, "shape_box"); break; }
-      if (vsbh::boxes_intersect(a, b) != segmentation::ShapeDescriptorBoxesIntersect(ra, rb)) fail((int)k, "boxes_intersect");
+      if (vsbs::boxes_intersect(a, b) != segmentation::ShapeDescriptorBoxesIntersect(ra, rb)) fail((int)k, "boxes_intersect");
     }
   }
   if (msg && msg_cap > 0) {

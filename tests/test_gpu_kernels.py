@@ -246,3 +246,67 @@ def test_region_hist_on_the_engine_output(K):
     exact, wsum = ob.region_hist([ob.bgr2lab(f) for f in clip], ids, nr, exact=True)
     assert np.array_equal(w.cpu().numpy(), wsum.astype(np.float32)) and int(wsum.sum()) == 6 * 160 * 120
     assert np.abs(hist.cpu().numpy() - exact).max() <= 1e-7
+
+
+def _moments_f32(ys, lxs, rxs):
+    """ShapeMomentsFromRasterization (segment_util/segmentation_util.cpp:652-693) in float32, interval by interval."""
+    f = np.float32
+    area = sx = sy = sxx = syy = sxy = f(0)
+    for y, lx, rx in zip(ys, lxs, rxs):
+        m, n, cy = f(lx), f(rx), f(y)
+        ln = f(n - m + f(1))
+        area = f(area + ln)
+        cx = f(f(n + m) * f(0.5))
+        row_x, row_y = f(cx * ln), f(cy * ln)
+        sx, sy = f(sx + row_x), f(sy + row_y)
+        sxy, syy = f(sxy + f(cy * row_x)), f(syy + f(cy * row_y))
+        poly = f(f(f(f(-m + f(f(f(2) * m) * m)) + n) + f(f(f(2) * m) * n)) + f(f(f(2) * n) * n))
+        sxx = f(sxx + f(f(ln * poly) / f(6)))
+    inv = f(f(1) / area)
+    return [f(sx * inv), f(sy * inv), f(sxx * inv), f(sxy * inv), f(syy * inv)]
+
+
+@pytest.mark.parametrize("shape,n_labels,seed", [((3, 40, 56), 4, 1), ((2, 97, 131), 7, 2), ((1, 8, 2100), 3, 3), ((4, 33, 33), 2, 4)])
+def test_label_components_and_moments(K, shape, n_labels, seed):
+    """K11 + K10 (csrc/shape.cu): components of every label in every frame against scipy's 4-connected labelling, numbered
+    in the order of their first scan interval; area, interval count and the float32 moments of every component
+    against an interval-by-interval restatement of ShapeMomentsFromRasterization (bit exact).  The engine tests
+    compare the same numbers, as fields of the output message, with the oracle and the reference."""
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    s, h, w = shape
+    coarse = rng.integers(0, n_labels, (s, (h + 5) // 6, (w + 5) // 6))
+    labels = np.kron(coarse, np.ones((1, 6, 6), np.int64))[:, :h, :w]
+    noise = rng.random((s, h, w)) < 0.08                         # specks: many small components
+    labels = np.where(noise, rng.integers(0, n_labels, (s, h, w)), labels).astype(np.int32)
+    comp, rec = K.label_components(_dev(labels))
+    comp = comp.cpu().numpy()
+    # expected numbering: components of all labels, ordered by (slice, first pixel in raster order)
+    expected = np.full((s, h, w), -1, np.int64)
+    firsts = []
+    for k in range(s):
+        for lab in range(n_labels):
+            lab_map, n = ndimage.label(labels[k] == lab, structure=[[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+            for c in range(1, n + 1):
+                first = np.flatnonzero(lab_map.ravel() == c)[0]
+                firsts.append((k, first, lab, c))
+    firsts.sort()
+    per_slice_maps = {}
+    for idx, (k, first, lab, c) in enumerate(firsts):
+        if (k, lab) not in per_slice_maps:
+            per_slice_maps[(k, lab)] = ndimage.label(labels[k] == lab, structure=[[0, 1, 0], [1, 1, 1], [0, 1, 0]])[0]
+        expected[k][per_slice_maps[(k, lab)] == c] = idx
+    assert len(firsts) == len(rec["label"])
+    assert np.array_equal(comp, expected)
+    assert np.array_equal(rec["label"], [f[2] for f in firsts]) and np.array_equal(rec["slice"], [f[0] for f in firsts])
+    for idx in range(len(firsts)):
+        mask = expected[rec["slice"][idx]] == idx
+        assert rec["area"][idx] == mask.sum()
+        ys, lxs, rxs = [], [], []
+        for y in np.flatnonzero(mask.any(axis=1)):
+            row = np.flatnonzero(np.diff(np.concatenate([[0], mask[y].astype(np.int8), [0]])))
+            for a, b in zip(row[0::2], row[1::2]):
+                ys.append(y); lxs.append(a); rxs.append(b - 1)
+        assert rec["count"][idx] == len(ys)
+        want = np.array(_moments_f32(ys, lxs, rxs), np.float32)
+        assert np.array_equal(rec["moments"][idx].view(np.uint32), want.view(np.uint32)), (idx, rec["moments"][idx], want)

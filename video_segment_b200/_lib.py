@@ -59,7 +59,7 @@ EXPORTED_SYMBOLS = [
     "vsb200_dense_last_id_map", "vsb200_dense_last_proto", "vsb200_dense_stats",
     "vsb200_dense_destroy", "vsb200_dense_export_halo", "vsb200_dense_import_halo",
     "vsb200_preprocess_scratch_bytes", "vsb200_preprocess", "vsb200_edge_build",
-    "vsb200_bucket_index", "vsb200_sort_edges", "vsb200_sort_scratch_bytes", "vsb200_segment_chunk",
+    "vsb200_bucket_index", "vsb200_sort_edges", "vsb200_sort_scratch_bytes", "vsb200_segment_chunk", "vsb200_label_components",
     "vsb200_bgr2lab", "vsb200_region_hist_scratch_bytes", "vsb200_region_hist_reset", "vsb200_region_hist_add",
     "vsb200_region_hist_finish", "vsb200_hist_chisquare",
     "vsb200_seg_writer_open", "vsb200_seg_writer_add", "vsb200_seg_writer_add_last_frame", "vsb200_seg_writer_write_chunk",
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         "vsb200_sort_scratch_bytes": ([C.c_int, C.c_int, C.c_int], C.c_size_t),
         "vsb200_sort_edges": ([C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp], C.c_int),
         "vsb200_segment_chunk": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_double), vp], C.c_int),
+        "vsb200_label_components": ([vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int), vp], C.c_int),
         "vsb200_dense_create": ([C.POINTER(DenseOpts), C.c_int, C.c_int, C.c_int, C.POINTER(vp)], C.c_int),
         "vsb200_dense_push": ([vp, vp, C.c_int, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)], C.c_int),
         "vsb200_dense_push_device": ([vp, vp, C.c_int, C.c_int64, C.POINTER(C.c_int)], C.c_int),

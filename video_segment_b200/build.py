@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvsb200.so")
-SOURCES = ["preprocess.cu", "edges.cu", "sort.cu", "merge.cu", "results.cu", "region_hist.cu", "region_stage.cu", "shard.cu", "capi_kernels.cu", "engine.cu", "pb_io.cu"]
+SOURCES = ["preprocess.cu", "edges.cu", "sort.cu", "merge.cu", "results.cu", "region_hist.cu", "region_stage.cu", "shard.cu", "shape.cu", "capi_kernels.cu", "engine.cu", "pb_io.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",

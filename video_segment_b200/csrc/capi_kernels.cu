@@ -12,6 +12,7 @@
 #include "../../include/vsb200.h"
 #include "common.cuh"
 #include "results.cuh"
+#include "shape.cuh"
 
 using namespace vsb;
 
@@ -227,6 +228,81 @@ int vsb200_segment_chunk(const float* dev_frames, int width, int height, int slo
     }
   } while (0);
   for (auto& e : ev) cudaEventDestroy(e);
+  cleanup();
+  return rc;
+}
+
+
+// K11 + K10 of csrc/shape.cu on a label volume (kernel-level entry for the parity tests): runs -> N4 components of every
+// label in every frame -> one record per component, components numbered in the order of their first scan interval.
+int vsb200_label_components(const int32_t* dev_labels, int width, int height, int slices, int32_t* dev_component_out,
+                            int32_t* host_records_out, int record_cap, int* n_components_out, void* stream) {
+  if (!dev_labels || width <= 0 || height <= 0 || slices <= 0 || !n_components_out) { set_error("label_components: bad arguments"); return VSB200_ERR_INVALID; }
+  if (int rc = require_device()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rows = slices * height;
+  int* d_slice_ids = nullptr; unsigned *d_counts = nullptr, *d_offsets = nullptr, *d_total = nullptr, *d_ngroups = nullptr;
+  RunRec* d_runs = nullptr; int *d_parent = nullptr, *d_group_of_run = nullptr, *d_iota = nullptr;
+  unsigned *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr}, *d_hist = nullptr, *d_tc = nullptr, *d_tb = nullptr;
+  RunGroup* d_groups = nullptr; int3* d_iv = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    for (void* p : {(void*)d_slice_ids, (void*)d_counts, (void*)d_offsets, (void*)d_total, (void*)d_ngroups, (void*)d_runs, (void*)d_parent,
+                    (void*)d_group_of_run, (void*)d_iota, (void*)d_keys[0], (void*)d_keys[1], (void*)d_vals[0], (void*)d_vals[1], (void*)d_hist,
+                    (void*)d_tc, (void*)d_tb, (void*)d_groups, (void*)d_iv})
+      if (p) cudaFree(p);
+  };
+#define LC_CUDA(expr) do { if ((expr) != cudaSuccess) { set_error("label_components: %s failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); rc = VSB200_ERR_CUDA; goto done; } } while (0)
+#define LC_RC(expr) do { if ((rc = (expr))) goto done; } while (0)
+  {
+    std::vector<int> ids(slices);
+    for (int k = 0; k < slices; ++k) ids[k] = k;
+    unsigned n_runs = 0, n_groups = 0;
+    LC_CUDA(cudaMalloc(&d_slice_ids, sizeof(int) * slices));
+    LC_CUDA(cudaMalloc(&d_counts, sizeof(unsigned) * rows));
+    LC_CUDA(cudaMalloc(&d_offsets, sizeof(unsigned) * rows));
+    LC_CUDA(cudaMalloc(&d_total, sizeof(unsigned)));
+    LC_CUDA(cudaMalloc(&d_ngroups, sizeof(unsigned)));
+    LC_CUDA(cudaMemcpyAsync(d_slice_ids, ids.data(), sizeof(int) * slices, cudaMemcpyHostToDevice, s));
+    LC_RC(launch_rle_count(dev_labels, width, height, d_slice_ids, slices, d_counts, s));
+    LC_RC(launch_scan_u32(d_counts, d_offsets, d_total, rows, s));
+    LC_CUDA(cudaMemcpyAsync(&n_runs, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    LC_CUDA(cudaStreamSynchronize(s));
+    const size_t cap = (size_t)n_runs + 16;
+    LC_CUDA(cudaMalloc(&d_runs, cap * sizeof(RunRec)));
+    LC_CUDA(cudaMalloc(&d_parent, cap * sizeof(int)));
+    LC_CUDA(cudaMalloc(&d_group_of_run, cap * sizeof(int)));
+    LC_CUDA(cudaMalloc(&d_iota, cap * sizeof(int)));
+    for (int k = 0; k < 2; ++k) { LC_CUDA(cudaMalloc(&d_keys[k], cap * sizeof(unsigned))); LC_CUDA(cudaMalloc(&d_vals[k], cap * sizeof(unsigned))); }
+    LC_CUDA(cudaMalloc(&d_hist, (cap / 2048 + 2) * 512 * sizeof(unsigned)));
+    LC_CUDA(cudaMalloc(&d_tc, (cap / 1024 + 2) * sizeof(unsigned)));
+    LC_CUDA(cudaMalloc(&d_tb, (cap / 1024 + 2) * sizeof(unsigned)));
+    LC_CUDA(cudaMalloc(&d_groups, cap * sizeof(RunGroup)));
+    LC_CUDA(cudaMalloc(&d_iv, cap * sizeof(int3)));
+    LC_RC(launch_rle_write(dev_labels, width, height, d_slice_ids, slices, d_offsets, d_runs, s));
+    LC_RC(launch_run_components(d_runs, n_runs, d_offsets, height, 0, d_parent, d_keys[0], d_vals[0], s));
+    unsigned *sk = nullptr, *sv = nullptr;
+    int bits = 1;
+    while ((1ull << bits) < n_runs) ++bits;
+    LC_RC(launch_sort_pairs(d_keys[0], d_vals[0], d_keys[1], d_vals[1], n_runs, bits, d_hist, d_total, &sk, &sv, s));
+    LC_RC(launch_group_runs(sk, sv, n_runs, d_runs, 0, d_tc, d_tb, d_ngroups, d_groups, d_group_of_run, d_iv, s));
+    LC_CUDA(cudaMemcpyAsync(&n_groups, d_ngroups, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    LC_CUDA(cudaStreamSynchronize(s));
+    *n_components_out = (int)n_groups;
+    if (dev_component_out) {
+      LC_RC(launch_init_iota(d_iota, (long long)n_groups, s));
+      LC_RC(launch_relabel_groups(d_runs, n_runs, d_group_of_run, d_iota, width, height, dev_component_out, s));
+    }
+    if (host_records_out && record_cap > 0) {
+      static_assert(sizeof(RunGroup) == 40, "record layout");
+      const size_t n_copy = std::min<size_t>(n_groups, (size_t)record_cap);
+      LC_CUDA(cudaMemcpyAsync(host_records_out, d_groups, n_copy * sizeof(RunGroup), cudaMemcpyDeviceToHost, s));
+    }
+    LC_CUDA(cudaStreamSynchronize(s));
+  }
+done:
+#undef LC_CUDA
+#undef LC_RC
   cleanup();
   return rc;
 }

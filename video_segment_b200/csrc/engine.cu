@@ -18,13 +18,28 @@
 
 #include "../../include/vsb200.h"
 #include "common.cuh"
-#include "host_shape.hpp"
 #include "results.cuh"
+#include "shape.cuh"
+#include "tubes.hpp"
 
 using namespace vsb;
-using vsbh::Region;
 
 namespace {
+
+// One over-segmentation region of the current chunk (RegionInformation, segmentation_common.h:39-116).
+struct Region {
+  int index = -1;          // position in the chunk's region list (first-seen order)
+  int label = -1;          // device label (representative node id, or a fresh id for a split-off tube)
+  int size = 0;
+  int constrained_id = -1;
+  int region_id = -1;
+  bool removed = false;    // FLAGGED_FOR_REMOVAL
+  std::vector<int> neighbors;                       // sorted region indices
+  std::vector<vsbt::Piece> pieces;                  // its N4 components, ascending by (frame, first scan interval)
+  std::vector<std::pair<int, int>> frames;          // (frame, area in that frame), ascending
+};
+
+int bits_for(unsigned long long n) { int b = 1; while ((1ull << b) < n) ++b; return b; }
 
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -80,6 +95,14 @@ struct vsb200_dense {
   int* d_slice_ids = nullptr; unsigned* d_row_counts = nullptr; unsigned* d_row_offsets = nullptr;
   unsigned* d_total = nullptr;
   RunRec* d_runs = nullptr; size_t runs_cap = 0;
+  // shape stage (shape.cu): components of the runs, the two sorted run orders and their groups
+  int* d_cc_parent = nullptr; int* d_group_of_run = nullptr; int* d_group_tab = nullptr;
+  unsigned* d_skeys[2] = {nullptr, nullptr}; unsigned* d_svals[2] = {nullptr, nullptr};
+  unsigned* d_shist = nullptr; unsigned* d_tile_counts = nullptr; unsigned* d_tile_bases = nullptr; unsigned* d_ngroups = nullptr;
+  RunGroup* d_groups[2] = {nullptr, nullptr}; int3* d_intervals[2] = {nullptr, nullptr};
+  size_t shape_cap = 0;
+  RunGroup* h_groups[2] = {nullptr, nullptr}; size_t h_groups_cap[2] = {0, 0};     // pinned
+  vsbs::Interval* h_intervals[2] = {nullptr, nullptr}; size_t h_intervals_cap[2] = {0, 0};
   int* d_tmp_ids = nullptr; int2* d_tmp_info = nullptr; size_t tmp_cap = 0;
   unsigned long long* d_pair_table = nullptr; unsigned long long* d_pairs = nullptr; unsigned long long* d_pair_count = nullptr;
   unsigned pair_table_cap = 1u << 22; unsigned long long pairs_cap = 1u << 21;
@@ -109,6 +132,8 @@ struct vsb200_dense {
   int segment_and_output(bool flush_all, std::vector<std::unique_ptr<FrameOut>>* results);
   int merge_constrained_regions(int slots);
   int upload_id_map(const FrameOut& f, int* dst);
+  int ensure_shape_capacity(size_t n_runs);
+  int ensure_host_groups(int which, size_t n_groups, size_t n_runs);
 };
 
 void vsb200_dense::release() {
@@ -118,6 +143,12 @@ void vsb200_dense::release() {
   F(d_labels); F(d_roots); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
   F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
   F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
+  F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
+  for (int k = 0; k < 2; ++k) {
+    F(d_skeys[k]); F(d_svals[k]); F(d_groups[k]); F(d_intervals[k]);
+    if (h_groups[k]) cudaFreeHost(h_groups[k]);
+    if (h_intervals[k]) cudaFreeHost(h_intervals[k]);
+  }
   for (auto p : d_frames) F(p);
   for (auto p : d_spatial) F(p);
   for (auto p : d_temporal) F(p);
@@ -189,6 +220,50 @@ int vsb200_dense::init() {
   ENG_CUDA(cudaMalloc(&d_con_ids[0], (size_t)n * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_con_ids[1], (size_t)n * sizeof(int)));
   ENG_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// Device buffers of the shape stage, sized by the number of scan intervals of the chunk.
+int vsb200_dense::ensure_shape_capacity(size_t n_runs) {
+  if (n_runs <= shape_cap) return 0;
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
+  for (int k = 0; k < 2; ++k) { F(d_skeys[k]); F(d_svals[k]); F(d_groups[k]); F(d_intervals[k]); }
+  shape_cap = 0;
+  const size_t cap = n_runs + n_runs / 2 + 4096;
+  ENG_CUDA(cudaMalloc(&d_cc_parent, cap * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_group_of_run, cap * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_group_tab, cap * 2 * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_shist, (cap / 2048 + 2) * 512 * sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_tile_counts, (cap / 1024 + 2) * sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_tile_bases, (cap / 1024 + 2) * sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_ngroups, sizeof(unsigned)));
+  for (int k = 0; k < 2; ++k) {
+    ENG_CUDA(cudaMalloc(&d_skeys[k], cap * sizeof(unsigned)));
+    ENG_CUDA(cudaMalloc(&d_svals[k], cap * sizeof(unsigned)));
+    ENG_CUDA(cudaMalloc(&d_groups[k], cap * sizeof(RunGroup)));
+    ENG_CUDA(cudaMalloc(&d_intervals[k], cap * sizeof(int3)));
+  }
+  shape_cap = cap;
+  return 0;
+}
+
+// Pinned host copies of one pass's groups and intervals.
+int vsb200_dense::ensure_host_groups(int which, size_t n_groups, size_t n_runs) {
+  if (n_groups > h_groups_cap[which]) {
+    if (h_groups[which]) cudaFreeHost(h_groups[which]);
+    h_groups[which] = nullptr; h_groups_cap[which] = 0;
+    const size_t cap = n_groups + n_groups / 2 + 1024;
+    ENG_CUDA(cudaMallocHost(&h_groups[which], cap * sizeof(RunGroup)));
+    h_groups_cap[which] = cap;
+  }
+  if (n_runs > h_intervals_cap[which]) {
+    if (h_intervals[which]) cudaFreeHost(h_intervals[which]);
+    h_intervals[which] = nullptr; h_intervals_cap[which] = 0;
+    const size_t cap = n_runs + n_runs / 2 + 4096;
+    ENG_CUDA(cudaMallocHost(&h_intervals[which], cap * sizeof(vsbs::Interval)));
+    h_intervals_cap[which] = cap;
+  }
   return 0;
 }
 
@@ -595,36 +670,58 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
   }
   ENG_RC(launch_rle_write(d_idimg, w, h, d_slice_ids, ns, d_row_offsets, d_runs, stream));
-  std::vector<RunRec> runs(n_runs);
-  ENG_CUDA(cudaMemcpyAsync(runs.data(), d_runs, sizeof(RunRec) * n_runs, cudaMemcpyDeviceToHost, stream));
-  d2h_bytes += (double)sizeof(RunRec) * n_runs + sizeof(h_bstart) + 64;
+  // ---------------- K11 + K10 on the device (shape.cu): components of every region in every frame, their moments ----------------
+  const int slice0 = slice_ids[0];
+  ENG_RC(ensure_shape_capacity(n_runs));
+  ENG_RC(launch_run_components(d_runs, n_runs, d_row_offsets, h, slice0, d_cc_parent, d_skeys[0], d_svals[0], stream));
+  unsigned *sorted_keys = nullptr, *sorted_vals = nullptr;
+  const int comp_bits = bits_for(n_runs);
+  ENG_RC(launch_sort_pairs(d_skeys[0], d_svals[0], d_skeys[1], d_svals[1], n_runs, comp_bits, d_shist, d_total, &sorted_keys, &sorted_vals, stream));
+  ENG_RC(launch_group_runs(sorted_keys, sorted_vals, n_runs, d_runs, 0, d_tile_counts, d_tile_bases, d_ngroups, d_groups[0],
+                           d_group_of_run, d_intervals[0], stream));
+  unsigned n_comps = 0;
+  ENG_CUDA(cudaMemcpyAsync(&n_comps, d_ngroups, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
   unsigned long long h_stats[8];
   ENG_CUDA(cudaMemcpyAsync(h_stats, mp.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  ENG_RC(ensure_host_groups(0, n_comps, n_runs));
+  ENG_CUDA(cudaMemcpyAsync(h_groups[0], d_groups[0], sizeof(RunGroup) * n_comps, cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaMemcpyAsync(h_intervals[0], d_intervals[0], sizeof(int3) * n_runs, cudaMemcpyDeviceToHost, stream));
+  d2h_bytes += (double)sizeof(RunGroup) * n_comps + (double)sizeof(int3) * n_runs + sizeof(h_bstart) + 64;
   cudaEventRecord(ev[3], stream);
   ENG_CUDA(cudaStreamSynchronize(stream));
-  stats[7] += 6;
+  stats[7] += 6 + 3 + 3 * ((comp_bits + 7) / 8) + 3;
   stats[8] += (double)h_stats[0];
   const double t_host0 = now_ms();
   // ---------------- regions in first-seen order (ObtainResults, :533-559) ----------------
+  // components arrive ascending by their first run, so the first component of a label is the label's first run
   std::vector<std::unique_ptr<Region>> regions;
   std::unordered_map<int, int> label2region;
   label2region.reserve(1 << 14);
-  for (const RunRec& r : runs) {
-    auto it = label2region.find(r.id);
+  std::vector<int> region_of_group(n_comps);
+  for (unsigned g = 0; g < n_comps; ++g) {
+    const RunGroup& c = h_groups[0][g];
+    auto it = label2region.find(c.tag);
     int ri;
     if (it == label2region.end()) {
       ri = (int)regions.size();
-      label2region[r.id] = ri;
+      label2region[c.tag] = ri;
       regions.emplace_back(new Region);
       regions.back()->index = ri;
-      regions.back()->label = r.id;
+      regions.back()->label = c.tag;
     } else {
       ri = it->second;
     }
+    region_of_group[g] = ri;
+    vsbt::Piece piece;
+    piece.frame = c.slice; piece.group = (int)g;
+    piece.moments.size = (float)c.area; piece.moments.mean_x = c.mean_x; piece.moments.mean_y = c.mean_y;
+    piece.moments.xx = c.xx; piece.moments.xy = c.xy; piece.moments.yy = c.yy;
+    piece.intervals = h_intervals[0] + c.first; piece.n_intervals = c.count;
     Region& R = *regions[ri];
-    if (R.raster.empty() || R.raster.back().frame < r.slice)
-      R.raster.push_back(vsbh::Slice{r.slice, std::make_shared<vsbh::Raster>()});
-    R.raster.back().raster->push_back(vsbh::Interval{r.y, r.left_x, r.right_x});
+    R.pieces.push_back(piece);
+    if (R.frames.empty() || R.frames.back().first < c.slice) R.frames.emplace_back(c.slice, 0);
+    R.frames.back().second += c.area;
   }
   // sizes / constraints of the representatives (GetCreateRegionInformation + size_adjust_map)
   {
@@ -646,21 +743,21 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     for (int i = 0; i < m; ++i) { regions[i]->size = info[i].x; regions[i]->constrained_id = info[i].y; }
     stats[7] += 1;
   }
-  // ---------------- EnforceSpatialConnectedness (:666-904) ----------------
-  std::vector<RunRec> relabel;
+  // ---------------- EnforceSpatialConnectedness (:666-904): tube decisions on the host over the components ----------------
+  std::vector<int> label_of_group;                 // fresh label of every component that leaves its region; empty = no split
   if (o.enforce_spatial_connectedness) {
     std::vector<const float*> flows;
     if (use_flow) for (int s = 0; s < slots; ++s) flows.push_back(h_flows[s].empty() ? nullptr : h_flows[s].data());
     int next_label = (int)nodes;
     const int num_regions = (int)regions.size();
     // the per-region tube analysis is independent: host worker threads (the reference runs it serially)
-    std::vector<std::vector<vsbh::Tube>> all_tubes(num_regions);
+    std::vector<std::vector<vsbt::Tube>> all_tubes(num_regions);
     {
       const int nt = std::max(1, std::min<int>(host_threads, num_regions));
       std::atomic<int> next_region{0};
       auto work = [&]() {
         for (int r = next_region.fetch_add(1); r < num_regions; r = next_region.fetch_add(1))
-          all_tubes[r] = vsbh::split_region_into_tubes(regions[r]->raster, w, h, use_flow ? &flows : nullptr);
+          all_tubes[r] = vsbt::TubeSplitter(regions[r]->pieces, w, h, use_flow ? &flows : nullptr).run();
       };
       std::vector<std::thread> pool;
       for (int t = 1; t < nt; ++t) pool.emplace_back(work);
@@ -668,9 +765,9 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
       for (auto& th : pool) th.join();
     }
     for (int r = 0; r < num_regions; ++r) {
-      std::vector<vsbh::Tube>& tubes = all_tubes[r];
+      std::vector<vsbt::Tube>& tubes = all_tubes[r];
       if (tubes.empty()) continue;
-      int keep = -1, keep_score = 0;
+      int keep = -1, keep_score = 0;                // the largest tube keeps the region's identity
       std::vector<float> areas(tubes.size());
       for (int k = 0; k < (int)tubes.size(); ++k) {
         float area = 0;
@@ -678,6 +775,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
         areas[k] = area;
         if (area > keep_score) { keep_score = area; keep = k; }
       }
+      const std::vector<vsbt::Piece> pieces = regions[r]->pieces;
       for (int k = 0; k < (int)tubes.size(); ++k) {
         Region* target = regions[r].get();
         if (k != keep) {
@@ -689,29 +787,74 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
           target->size = areas[k];
           target->constrained_id = -1;
           label2region[target->label] = target->index;
-          for (const auto& s : tubes[k])
-            for (const auto& iv : s.raster) relabel.push_back(RunRec{s.frame, iv.y, iv.lx, iv.rx, target->label});
+          if (label_of_group.empty()) label_of_group.assign(n_comps, -1);
         }
-        target->raster.clear();
-        for (auto& s : tubes[k]) {
-          auto nr = std::make_shared<vsbh::Raster>();
-          nr->swap(s.raster);
-          target->raster.push_back(vsbh::Slice{s.frame, nr});
+        target->pieces.clear();
+        target->frames.clear();
+        for (const auto& s : tubes[k]) {
+          target->frames.emplace_back(s.frame, s.shape.size);
+          for (int pi : s.pieces) {
+            target->pieces.push_back(pieces[pi]);
+            if (k != keep) { label_of_group[pieces[pi].group] = target->label; region_of_group[pieces[pi].group] = target->index; }
+          }
         }
       }
     }
   }
-  stats[5] += now_ms() - t_host0;
-  // ---------------- neighbours (DetermineNeighborIdsImpl, segmentation_graph.h:466-496) ----------------
-  if (!relabel.empty()) {
-    if (relabel.size() > runs_cap) {
-      if (d_runs) cudaFree(d_runs);
-      runs_cap = relabel.size() * 2;
-      ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
-    }
-    ENG_CUDA(cudaMemcpyAsync(d_runs, relabel.data(), sizeof(RunRec) * relabel.size(), cudaMemcpyHostToDevice, stream));
-    ENG_RC(launch_relabel(d_runs, (int)relabel.size(), w, h, d_labels, stream));
+  // ---------------- result shaping, part 1 (dense_segmentation.cpp:335-398): which regions, which ids, which order ----------------
+  const int overlap_start = slots - (flush_all ? 0 : overlap_frames);
+  const int last_output_frame = std::min(slots - 1, overlap_start);
+  const int max_result_frame = std::min(slots - 1, last_output_frame + constraint_frames);
+  // ConstrainSegmentationToFrameInterval(0, last_output_frame + 1) (segmentation.cpp:392-403)
+  for (auto& R : regions)
+    if (R->frames.empty() || R->frames.front().first >= last_output_frame + 1 || R->frames.back().first < 0) R->removed = true;
+  // AdjustRegionAreaToFrameInterval (segmentation.cpp:424-441)
+  for (auto& R : regions)
+    for (const auto& fr : R->frames)
+      if (fr.first < 0 || fr.first >= last_output_frame + 1) R->size -= fr.second;
+  // AssignUniqueRegionIds (segmentation.cpp:549-582)
+  const bool use_constraints = constrained_chunk;
+  int max_id = -1;
+  for (auto& R : regions) {
+    R->region_id = (use_constraints && R->constrained_id >= 0) ? R->constrained_id : R->index + max_region_id;
+    max_id = std::max(max_id, R->region_id);
   }
+  max_region_id = std::max(max_region_id, max_id + 1);
+  // order of the regions inside a frame of the result: list order, or ascending id once ids come from constraints
+  const unsigned n_ranks = (unsigned)regions.size();
+  std::vector<int> region_at_rank(n_ranks);
+  for (unsigned k = 0; k < n_ranks; ++k) region_at_rank[k] = (int)k;
+  if (use_constraints)
+    std::stable_sort(region_at_rank.begin(), region_at_rank.end(),
+                     [&](int a, int b) { return regions[a]->region_id < regions[b]->region_id; });
+  if ((unsigned long long)ns * n_ranks >= (1ull << 32)) { set_error("%u regions x %d frames overflow the result sort key", n_ranks, ns); return VSB200_ERR_CAPACITY; }
+  {
+    std::vector<int> rank_of_region(n_ranks);
+    for (unsigned k = 0; k < n_ranks; ++k) rank_of_region[region_at_rank[k]] = (int)k;
+    std::vector<int> rank_of_group(n_comps);
+    for (unsigned g = 0; g < n_comps; ++g) rank_of_group[g] = rank_of_region[region_of_group[g]];
+    ENG_CUDA(cudaMemcpyAsync(d_group_tab, rank_of_group.data(), sizeof(int) * n_comps, cudaMemcpyHostToDevice, stream));
+    if (!label_of_group.empty())
+      ENG_CUDA(cudaMemcpyAsync(d_group_tab + n_comps, label_of_group.data(), sizeof(int) * n_comps, cudaMemcpyHostToDevice, stream));
+    ENG_CUDA(cudaStreamSynchronize(stream));        // the tables are stack vectors
+  }
+  stats[5] += now_ms() - t_host0;
+  // split-off tubes get their fresh labels in the label volume (:866-893), then every run its place in the result:
+  // (frame, rank of its region), stable, so that a region's intervals stay in raster order; K10 over that order gives the
+  // ShapeMoments of every region in every frame and the interval arrays of the output, ready to copy
+  if (!label_of_group.empty()) {
+    ENG_RC(launch_relabel_groups(d_runs, n_runs, d_group_of_run, d_group_tab + n_comps, w, h, d_labels, stream));
+    stats[7] += 1;
+  }
+  const int result_bits = bits_for((unsigned long long)ns * n_ranks);
+  ENG_RC(launch_result_keys(d_runs, n_runs, d_group_of_run, d_group_tab, slice0, n_ranks, d_skeys[0], d_svals[0], stream));
+  ENG_RC(launch_sort_pairs(d_skeys[0], d_svals[0], d_skeys[1], d_svals[1], n_runs, result_bits, d_shist, d_total, &sorted_keys, &sorted_vals, stream));
+  ENG_RC(launch_group_runs(sorted_keys, sorted_vals, n_runs, d_runs, 1, d_tile_counts, d_tile_bases, d_ngroups, d_groups[1],
+                           nullptr, d_intervals[1], stream));
+  unsigned n_slices_out = 0;
+  ENG_CUDA(cudaMemcpyAsync(&n_slices_out, d_ngroups, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+  stats[7] += 1 + 3 * ((result_bits + 7) / 8) + 3;
+  // ---------------- neighbours (DetermineNeighborIdsImpl, segmentation_graph.h:466-496) ----------------
   unsigned long long n_pairs = 0;
   for (int attempt = 0;; ++attempt) {
     ENG_RC(launch_neighbor_pairs(d_roots, d_labels, w, h, slots, use_flow ? d_flows : nullptr, constrained_chunk ? 1 : 0,
@@ -737,7 +880,11 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   cudaEventRecord(ev[4], stream);
   std::vector<unsigned long long> pairs(n_pairs);
   if (n_pairs) ENG_CUDA(cudaMemcpy(pairs.data(), d_pairs, sizeof(unsigned long long) * n_pairs, cudaMemcpyDeviceToHost));
-  d2h_bytes += 8.0 * n_pairs + 8.0 * regions.size();
+  ENG_RC(ensure_host_groups(1, n_slices_out, n_runs));
+  ENG_CUDA(cudaMemcpyAsync(h_groups[1], d_groups[1], sizeof(RunGroup) * n_slices_out, cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaMemcpyAsync(h_intervals[1], d_intervals[1], sizeof(int3) * n_runs, cudaMemcpyDeviceToHost, stream));
+  ENG_CUDA(cudaStreamSynchronize(stream));
+  d2h_bytes += 8.0 * n_pairs + 8.0 * regions.size() + (double)sizeof(RunGroup) * n_slices_out + (double)sizeof(int3) * n_runs;
   stats[7] += 3;
   const double t_host1 = now_ms();
   for (unsigned long long key : pairs) {
@@ -751,29 +898,18 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     std::sort(R->neighbors.begin(), R->neighbors.end());
     R->neighbors.erase(std::unique(R->neighbors.begin(), R->neighbors.end()), R->neighbors.end());
   }
-  // ---------------- result shaping (dense_segmentation.cpp:335-398) ----------------
-  const int overlap_start = slots - (flush_all ? 0 : overlap_frames);
-  const int last_output_frame = std::min(slots - 1, overlap_start);
-  const int max_result_frame = std::min(slots - 1, last_output_frame + constraint_frames);
-  // ConstrainSegmentationToFrameInterval(0, last_output_frame + 1) (segmentation.cpp:392-403)
-  for (auto& R : regions)
-    if (R->raster.empty() || R->raster.front().frame >= last_output_frame + 1 || R->raster.back().frame < 0) R->removed = true;
-  // AdjustRegionAreaToFrameInterval (segmentation.cpp:424-441)
-  for (auto& R : regions)
-    for (const auto& sl : R->raster)
-      if (sl.frame < 0 || sl.frame >= last_output_frame + 1) R->size -= vsbh::raster_area(*sl.raster);
-  // AssignUniqueRegionIds (segmentation.cpp:549-582)
-  const bool use_constraints = constrained_chunk;
-  int max_id = -1;
-  for (auto& R : regions) {
-    R->region_id = (use_constraints && R->constrained_id >= 0) ? R->constrained_id : R->index + max_region_id;
-    max_id = std::max(max_id, R->region_id);
-  }
-  max_region_id = std::max(max_region_id, max_id + 1);
+  // ---------------- result shaping, part 2: the frames of the result ----------------
   const int chunk_sz = last_output_frame - curr_chunk_start + 1;
   const int hierarchy_frame_idx = num_output_frames;
   const int n_out_frames = max_result_frame - curr_chunk_start + 1;
   std::vector<std::unique_ptr<FrameOut>> frame_outs(std::max(n_out_frames, 0));
+  std::vector<std::pair<unsigned, unsigned>> groups_of_slice(ns, std::make_pair(0u, 0u));
+  for (unsigned k = 0; k < n_slices_out;) {
+    unsigned e = k;
+    while (e < n_slices_out && h_groups[1][e].slice == h_groups[1][k].slice) ++e;
+    groups_of_slice[h_groups[1][k].slice - slice0] = std::make_pair(k, e);
+    k = e;
+  }
   auto build_frame = [&](int f) {
     // RetrieveSegmentation3D (segmentation.cpp:458-533)
     std::unique_ptr<FrameOut> out(new FrameOut);
@@ -781,25 +917,27 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     out->connectedness = o.enforce_n4_connectivity ? 1 : 2;
     out->chunk_size = chunk_sz; out->overlap_start = chunk_sz; out->hierarchy_frame_idx = hierarchy_frame_idx;
     out->pts = 0;
-    struct Item { int id; const vsbh::Raster* raster; };
-    std::vector<Item> items;
-    for (const auto& R : regions) {
-      auto it = std::lower_bound(R->raster.begin(), R->raster.end(), f,
-                                 [](const vsbh::Slice& a, int fr) { return a.frame < fr; });
-      if (it == R->raster.end() || it->frame != f) continue;
-      items.push_back(Item{R->region_id, it->raster.get()});
-    }
-    if (use_constraints) std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.id < b.id; });
+    // the groups of pass 1 with this frame: one per region present, in result order, intervals contiguous
+    const std::pair<unsigned, unsigned> span = groups_of_slice[f - slice0];
+    const size_t n_items = span.second - span.first;
+    out->region_id.reserve(n_items);
+    out->interval_offset.reserve(n_items + 1);
+    out->moments.reserve(n_items * 6);
     out->interval_offset.push_back(0);
-    for (const Item& it : items) {
-      out->region_id.push_back(it.id);
-      for (const auto& iv : *it.raster) {
-        out->intervals.push_back(iv.y); out->intervals.push_back(iv.lx); out->intervals.push_back(iv.rx);
+    if (n_items) {
+      const RunGroup& g0 = h_groups[1][span.first];
+      const RunGroup& g1 = h_groups[1][span.second - 1];
+      const size_t n_iv = (size_t)(g1.first + g1.count - g0.first);
+      out->intervals.resize(n_iv * 3);
+      memcpy(out->intervals.data(), h_intervals[1] + g0.first, n_iv * sizeof(vsbs::Interval));
+      for (unsigned k = span.first; k < span.second; ++k) {
+        const RunGroup& g = h_groups[1][k];
+        const unsigned rank = (unsigned)g.tag - (unsigned)(f - slice0) * n_ranks;
+        out->region_id.push_back(regions[region_at_rank[rank]]->region_id);
+        out->interval_offset.push_back((int32_t)(g.first + g.count - g0.first));
+        const float mm[6] = {(float)g.area, g.mean_x, g.mean_y, g.xx, g.xy, g.yy};
+        out->moments.insert(out->moments.end(), mm, mm + 6);
       }
-      out->interval_offset.push_back((int32_t)(out->intervals.size() / 3));
-      const vsbh::Moments mo = vsbh::moments_of(*it.raster);
-      const float mm[6] = {mo.size, mo.mx, mo.my, mo.xx, mo.xy, mo.yy};
-      out->moments.insert(out->moments.end(), mm, mm + 6);
     }
     out->neighbor_offset.push_back(0);
     if (f == curr_chunk_start) {                         // hierarchy level 0 (segmentation.cpp:702-773)
@@ -809,7 +947,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
         if (R->removed) continue;
         Comp c;
         c.id = R->region_id; c.size = R->size;
-        c.sf = R->raster.front().frame; c.ef = R->raster.back().frame;
+        c.sf = R->frames.front().first; c.ef = R->frames.back().first;
         for (int nb : R->neighbors) if (!regions[nb]->removed) c.nb.push_back(regions[nb]->region_id);
         if (use_constraints) std::sort(c.nb.begin(), c.nb.end());
         comps.push_back(std::move(c));

@@ -34,7 +34,7 @@
 
 #include "../../include/vsb200.h"
 #include "common.cuh"
-#include "host_shape.hpp"
+#include "region_raster.hpp"
 #include "region_kernels.cuh"
 
 using namespace vsb;
@@ -250,9 +250,9 @@ int grid_of(size_t items, int block) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-using vsbh::Raster;
-using vsbh::Raster3D;
-using vsbh::Slice;
+using vsbr::Raster;
+using vsbr::Raster3D;
+using vsbr::Slice;
 
 template <class T> bool insert_sorted_unique(const T& t, std::vector<T>* v) {
   auto pos = std::lower_bound(v->begin(), v->end(), t);
@@ -372,7 +372,7 @@ class ChunkSet {
       auto raster = std::make_shared<Raster>();
       for (int q = r.interval_offset[k]; q < r.interval_offset[k + 1]; ++q) {
         const int y = r.intervals[3 * q], lx = r.intervals[3 * q + 1], rx = r.intervals[3 * q + 2];
-        raster->push_back(vsbh::Interval{y, lx, rx});
+        raster->push_back(vsbr::Interval{y, lx, rx});
         dev_->h_runs[w++] = PaintRun{y, lx, rx, n->index};
       }
       n->raster->push_back(Slice{frame_number_, raster});
@@ -768,7 +768,7 @@ class Agglomeration {
       else if (fb < fa) { out->push_back(Slice{fb, std::make_shared<Raster>(*b[j].raster)}); ++j; }
       else {
         auto m = std::make_shared<Raster>();
-        vsbh::merge_rasters(*a[i].raster, *b[j].raster, m.get());
+        vsbr::merge_rasters(*a[i].raster, *b[j].raster, m.get());
         out->push_back(Slice{fa, m});
         ++i; ++j;
       }
@@ -865,7 +865,7 @@ void ChunkSet::adjust_area(int lhs, int rhs) {              // segmentation.cpp:
   for (auto& n : levels_[0]) {
     int inc = 0;
     if (!n->raster) continue;
-    for (const auto& s : *n->raster) if (s.frame < lhs || s.frame >= rhs) inc -= vsbh::raster_area(*s.raster);
+    for (const auto& s : *n->raster) if (s.frame < lhs || s.frame >= rhs) inc -= vsbr::raster_area(*s.raster);
     n->size += inc;
     prev[n->index] = inc;
   }
@@ -923,8 +923,8 @@ void ChunkSet::retrieve(int frame, bool with_hierarchy, FrameOutR* out) const {
     f.push_back(it.id);
     f.push_back((int32_t)it.raster->size());
     for (const auto& s : *it.raster) { f.push_back(s.y); f.push_back(s.lx); f.push_back(s.rx); }
-    const vsbh::Moments m = vsbh::moments_of(*it.raster);
-    for (float v : {m.size, m.mx, m.my, m.xx, m.xy, m.yy}) f.push_back(bits(v));
+    const vsbs::Moments m = vsbr::moments_of(*it.raster);
+    for (float v : {m.size, m.mean_x, m.mean_y, m.xx, m.xy, m.yy}) f.push_back(bits(v));
   }
   if (!with_hierarchy) return;
   std::unordered_map<int, std::pair<int, int>> prev_bound, cur_bound;

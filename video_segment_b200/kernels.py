@@ -120,3 +120,23 @@ def hist_chisquare(hist: torch.Tensor, pairs: torch.Tensor) -> torch.Tensor:
     check(lib().vsb200_hist_chisquare(_ptr(hist), hist.shape[1], _ptr(pairs), pairs.shape[0], _ptr(out), _stream()),
           "vsb200_hist_chisquare")
     return out
+
+
+def label_components(labels: torch.Tensor):
+    """K11 + K10 (csrc/shape.cu): N4 connected components of every label in every frame of an int32 label volume
+    (S, H, W) on the GPU and their shape moments -- ConnectedComponents(raster, N4_CONNECT) and
+    ShapeMomentsFromRasterization (segment_util/segmentation_util.cpp:1007-1101, 652-693) for all regions at once.
+    Returns (component map (S, H, W) int32 on the GPU, records): components are numbered in the order of their first
+    scan interval; records is a dict of numpy arrays first / count / label / slice / area (int32) and moments
+    (float32 [n, 5]: mean_x, mean_y, xx, xy, yy)."""
+    assert labels.is_cuda and labels.dtype == torch.int32 and labels.dim() == 3 and labels.is_contiguous()
+    s, h, w = labels.shape
+    comp = torch.full_like(labels, -1)
+    cap = s * h * w
+    rec = np.zeros((cap, 10), np.int32)
+    n = C.c_int(0)
+    check(lib().vsb200_label_components(_ptr(labels), w, h, s, _ptr(comp), rec.ctypes.data_as(C.c_void_p), cap, C.byref(n), _stream()),
+          "vsb200_label_components")
+    rec = rec[:n.value]
+    return comp, dict(first=rec[:, 0], count=rec[:, 1], label=rec[:, 2], slice=rec[:, 3], area=rec[:, 4],
+                      moments=np.ascontiguousarray(rec[:, 5:10]).view(np.float32))
