@@ -240,7 +240,7 @@ def ref_io_strip(d: dict, save_shape_moments: bool) -> bytes:
 
 
 def host_shape_check(seed: int, n_cases: int):
-    """(#mismatches, first mismatch) of csrc/host_shape.hpp against the reference's segmentation_util.cpp functions on
+    """(#mismatches, first mismatch) of csrc/shape_math.hpp + csrc/region_raster.hpp against the reference's segmentation_util.cpp functions on
     random rasters (tests/host_shape_check.cpp)."""
     L = host_lib()
     L.host_shape_check.argtypes = [C.c_uint, C.c_int, C.c_char_p, C.c_int]

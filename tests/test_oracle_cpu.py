@@ -443,9 +443,9 @@ def test_cpp_host_side_rebuilds_reference_messages(case):
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_product_host_shape_helpers_equal_reference_functions(seed):
-    """video_segment_b200/csrc/host_shape.hpp (the host-side region bookkeeping of the streaming engine: shape moments,
-    shape descriptors, raster merge, N4 connected components, oriented boxes) against the reference's own
-    segment_util/segmentation_util.cpp functions, compiled unmodified, on random rasters; floats by bits."""
+    """video_segment_b200/csrc/shape_math.hpp (the moment accumulator shared by the device kernel of shape.cu and the host,
+    shape descriptors, oriented boxes) and csrc/region_raster.hpp (raster union of the hierarchical stage) against the
+    reference's own segment_util/segmentation_util.cpp functions, compiled unmodified, on random rasters; floats by bits."""
     import reference_binding as rb
     if not rb.host_available():
         pytest.skip("oracle/_ref/libb200_host_check.so not built (needs /root/reference)")

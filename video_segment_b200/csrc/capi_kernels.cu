@@ -243,13 +243,13 @@ int vsb200_label_components(const int32_t* dev_labels, int width, int height, in
   const int rows = slices * height;
   int* d_slice_ids = nullptr; unsigned *d_counts = nullptr, *d_offsets = nullptr, *d_total = nullptr, *d_ngroups = nullptr;
   RunRec* d_runs = nullptr; int *d_parent = nullptr, *d_group_of_run = nullptr, *d_iota = nullptr;
-  unsigned *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr}, *d_hist = nullptr, *d_tc = nullptr, *d_tb = nullptr;
+  unsigned *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr}, *d_hist = nullptr, *d_tc = nullptr, *d_tb = nullptr, *d_hp = nullptr;
   RunGroup* d_groups = nullptr; int3* d_iv = nullptr;
   int rc = 0;
   auto cleanup = [&]() {
     for (void* p : {(void*)d_slice_ids, (void*)d_counts, (void*)d_offsets, (void*)d_total, (void*)d_ngroups, (void*)d_runs, (void*)d_parent,
                     (void*)d_group_of_run, (void*)d_iota, (void*)d_keys[0], (void*)d_keys[1], (void*)d_vals[0], (void*)d_vals[1], (void*)d_hist,
-                    (void*)d_tc, (void*)d_tb, (void*)d_groups, (void*)d_iv})
+                    (void*)d_tc, (void*)d_tb, (void*)d_hp, (void*)d_groups, (void*)d_iv})
       if (p) cudaFree(p);
   };
 #define LC_CUDA(expr) do { if ((expr) != cudaSuccess) { set_error("label_components: %s failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); rc = VSB200_ERR_CUDA; goto done; } } while (0)
@@ -277,6 +277,7 @@ int vsb200_label_components(const int32_t* dev_labels, int width, int height, in
     LC_CUDA(cudaMalloc(&d_hist, (cap / 2048 + 2) * 512 * sizeof(unsigned)));
     LC_CUDA(cudaMalloc(&d_tc, (cap / 1024 + 2) * sizeof(unsigned)));
     LC_CUDA(cudaMalloc(&d_tb, (cap / 1024 + 2) * sizeof(unsigned)));
+    LC_CUDA(cudaMalloc(&d_hp, cap * sizeof(unsigned)));
     LC_CUDA(cudaMalloc(&d_groups, cap * sizeof(RunGroup)));
     LC_CUDA(cudaMalloc(&d_iv, cap * sizeof(int3)));
     LC_RC(launch_rle_write(dev_labels, width, height, d_slice_ids, slices, d_offsets, d_runs, s));
@@ -285,7 +286,7 @@ int vsb200_label_components(const int32_t* dev_labels, int width, int height, in
     int bits = 1;
     while ((1ull << bits) < n_runs) ++bits;
     LC_RC(launch_sort_pairs(d_keys[0], d_vals[0], d_keys[1], d_vals[1], n_runs, bits, d_hist, d_total, &sk, &sv, s));
-    LC_RC(launch_group_runs(sk, sv, n_runs, d_runs, 0, d_tc, d_tb, d_ngroups, d_groups, d_group_of_run, d_iv, s));
+    LC_RC(launch_group_runs(sk, sv, n_runs, d_runs, 0, d_tc, d_tb, d_hp, d_ngroups, d_groups, d_group_of_run, d_iv, s));
     LC_CUDA(cudaMemcpyAsync(&n_groups, d_ngroups, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     LC_CUDA(cudaStreamSynchronize(s));
     *n_components_out = (int)n_groups;

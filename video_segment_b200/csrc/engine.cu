@@ -98,7 +98,7 @@ struct vsb200_dense {
   // shape stage (shape.cu): components of the runs, the two sorted run orders and their groups
   int* d_cc_parent = nullptr; int* d_group_of_run = nullptr; int* d_group_tab = nullptr;
   unsigned* d_skeys[2] = {nullptr, nullptr}; unsigned* d_svals[2] = {nullptr, nullptr};
-  unsigned* d_shist = nullptr; unsigned* d_tile_counts = nullptr; unsigned* d_tile_bases = nullptr; unsigned* d_ngroups = nullptr;
+  unsigned* d_shist = nullptr; unsigned* d_head_pos = nullptr; unsigned* d_tile_counts = nullptr; unsigned* d_tile_bases = nullptr; unsigned* d_ngroups = nullptr;
   RunGroup* d_groups[2] = {nullptr, nullptr}; int3* d_intervals[2] = {nullptr, nullptr};
   size_t shape_cap = 0;
   RunGroup* h_groups[2] = {nullptr, nullptr}; size_t h_groups_cap[2] = {0, 0};     // pinned
@@ -143,7 +143,7 @@ void vsb200_dense::release() {
   F(d_labels); F(d_roots); F(d_idimg); F(d_size_adjust); F(d_slice_ids); F(d_row_counts); F(d_row_offsets); F(d_total);
   F(d_runs); F(d_tmp_ids); F(d_tmp_info); F(d_pair_table); F(d_pairs); F(d_pair_count);
   F(d_con_ids[0]); F(d_con_ids[1]); F(d_first_of_id);
-  F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
+  F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_head_pos); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
   for (int k = 0; k < 2; ++k) {
     F(d_skeys[k]); F(d_svals[k]); F(d_groups[k]); F(d_intervals[k]);
     if (h_groups[k]) cudaFreeHost(h_groups[k]);
@@ -227,7 +227,7 @@ int vsb200_dense::init() {
 int vsb200_dense::ensure_shape_capacity(size_t n_runs) {
   if (n_runs <= shape_cap) return 0;
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
+  F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_head_pos); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
   for (int k = 0; k < 2; ++k) { F(d_skeys[k]); F(d_svals[k]); F(d_groups[k]); F(d_intervals[k]); }
   shape_cap = 0;
   const size_t cap = n_runs + n_runs / 2 + 4096;
@@ -235,6 +235,7 @@ int vsb200_dense::ensure_shape_capacity(size_t n_runs) {
   ENG_CUDA(cudaMalloc(&d_group_of_run, cap * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_group_tab, cap * 2 * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_shist, (cap / 2048 + 2) * 512 * sizeof(unsigned)));
+  ENG_CUDA(cudaMalloc(&d_head_pos, cap * sizeof(unsigned)));
   ENG_CUDA(cudaMalloc(&d_tile_counts, (cap / 1024 + 2) * sizeof(unsigned)));
   ENG_CUDA(cudaMalloc(&d_tile_bases, (cap / 1024 + 2) * sizeof(unsigned)));
   ENG_CUDA(cudaMalloc(&d_ngroups, sizeof(unsigned)));
@@ -664,6 +665,8 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   unsigned n_runs = 0;
   ENG_CUDA(cudaMemcpyAsync(&n_runs, d_total, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
   ENG_CUDA(cudaStreamSynchronize(stream));
+  const bool stage_debug = getenv("VSB200_STAGE_DEBUG") != nullptr;
+  const double t_dbg0 = now_ms();
   if (n_runs > runs_cap) {
     if (d_runs) cudaFree(d_runs);
     runs_cap = (size_t)n_runs + n_runs / 2 + 1024;
@@ -677,22 +680,26 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   unsigned *sorted_keys = nullptr, *sorted_vals = nullptr;
   const int comp_bits = bits_for(n_runs);
   ENG_RC(launch_sort_pairs(d_skeys[0], d_svals[0], d_skeys[1], d_svals[1], n_runs, comp_bits, d_shist, d_total, &sorted_keys, &sorted_vals, stream));
-  ENG_RC(launch_group_runs(sorted_keys, sorted_vals, n_runs, d_runs, 0, d_tile_counts, d_tile_bases, d_ngroups, d_groups[0],
+  ENG_RC(launch_group_runs(sorted_keys, sorted_vals, n_runs, d_runs, 0, d_tile_counts, d_tile_bases, d_head_pos, d_ngroups, d_groups[0],
                            d_group_of_run, d_intervals[0], stream));
   unsigned n_comps = 0;
   ENG_CUDA(cudaMemcpyAsync(&n_comps, d_ngroups, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
   unsigned long long h_stats[8];
   ENG_CUDA(cudaMemcpyAsync(h_stats, mp.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, stream));
   ENG_CUDA(cudaStreamSynchronize(stream));
+  const double t_dbg1 = now_ms();
   ENG_RC(ensure_host_groups(0, n_comps, n_runs));
   ENG_CUDA(cudaMemcpyAsync(h_groups[0], d_groups[0], sizeof(RunGroup) * n_comps, cudaMemcpyDeviceToHost, stream));
   ENG_CUDA(cudaMemcpyAsync(h_intervals[0], d_intervals[0], sizeof(int3) * n_runs, cudaMemcpyDeviceToHost, stream));
   d2h_bytes += (double)sizeof(RunGroup) * n_comps + (double)sizeof(int3) * n_runs + sizeof(h_bstart) + 64;
   cudaEventRecord(ev[3], stream);
   ENG_CUDA(cudaStreamSynchronize(stream));
-  stats[7] += 6 + 3 + 3 * ((comp_bits + 7) / 8) + 3;
+  stats[7] += 6 + 3 + 3 * ((comp_bits + 7) / 8) + 4;
   stats[8] += (double)h_stats[0];
   const double t_host0 = now_ms();
+  if (stage_debug)
+    fprintf(stderr, "[vsb200 stage] runs %u components %u: components+sort+moments %.2f ms, copy out %.2f ms\n", n_runs, n_comps,
+            t_dbg1 - t_dbg0, t_host0 - t_dbg1);
   // ---------------- regions in first-seen order (ObtainResults, :533-559) ----------------
   // components arrive ascending by their first run, so the first component of a label is the label's first run
   std::vector<std::unique_ptr<Region>> regions;
@@ -849,11 +856,11 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   const int result_bits = bits_for((unsigned long long)ns * n_ranks);
   ENG_RC(launch_result_keys(d_runs, n_runs, d_group_of_run, d_group_tab, slice0, n_ranks, d_skeys[0], d_svals[0], stream));
   ENG_RC(launch_sort_pairs(d_skeys[0], d_svals[0], d_skeys[1], d_svals[1], n_runs, result_bits, d_shist, d_total, &sorted_keys, &sorted_vals, stream));
-  ENG_RC(launch_group_runs(sorted_keys, sorted_vals, n_runs, d_runs, 1, d_tile_counts, d_tile_bases, d_ngroups, d_groups[1],
+  ENG_RC(launch_group_runs(sorted_keys, sorted_vals, n_runs, d_runs, 1, d_tile_counts, d_tile_bases, d_head_pos, d_ngroups, d_groups[1],
                            nullptr, d_intervals[1], stream));
   unsigned n_slices_out = 0;
   ENG_CUDA(cudaMemcpyAsync(&n_slices_out, d_ngroups, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-  stats[7] += 1 + 3 * ((result_bits + 7) / 8) + 3;
+  stats[7] += 1 + 3 * ((result_bits + 7) / 8) + 4;
   // ---------------- neighbours (DetermineNeighborIdsImpl, segmentation_graph.h:466-496) ----------------
   unsigned long long n_pairs = 0;
   for (int attempt = 0;; ++attempt) {

@@ -165,52 +165,79 @@ __global__ void __launch_bounds__(kHeadTile) group_heads_count_kernel(const unsi
   if (threadIdx.x == 0) tile_counts[blockIdx.x] = (unsigned)c;
 }
 
-// pass 0 (components): tag = label of the runs, group_of_run[run] = index of its group.  pass 1 (result order): tag = key.
-__global__ void __launch_bounds__(kHeadTile) group_runs_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals,
-                                                               unsigned n, const RunRec* __restrict__ runs,
-                                                               const unsigned* __restrict__ tile_bases, int pass,
-                                                               RunGroup* __restrict__ groups, int* __restrict__ group_of_run,
-                                                               int3* __restrict__ intervals) {
+// position of every group's first element in the sorted order
+__global__ void __launch_bounds__(kHeadTile) group_heads_write_kernel(const unsigned* __restrict__ keys, unsigned n,
+                                                                      const unsigned* __restrict__ tile_bases,
+                                                                      unsigned* __restrict__ head_pos) {
   __shared__ unsigned warp_heads[kHeadTile / 32];
   const unsigned i = blockIdx.x * kHeadTile + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned key = i < n ? keys[i] : 0u;
-  const bool head = i < n && (i == 0 || key != keys[i - 1]);
+  const bool head = i < n && (i == 0 || keys[i] != keys[i - 1]);
   const unsigned m = __ballot_sync(0xffffffffu, head);
   if (lane == 0) warp_heads[warp] = __popc(m);
   __syncthreads();
   if (!head) return;
   unsigned g = tile_bases[blockIdx.x] + __popc(m & ((1u << lane) - 1u));
   for (int k = 0; k < warp; ++k) g += warp_heads[k];
-  vsbs::MomentSum sum;
-  int area = 0;
-  unsigned p = i;
-  const RunRec first = runs[vals[i]];
-  for (; p < n && keys[p] == key; ++p) {
-    const unsigned run = vals[p];
-    const RunRec rr = runs[run];
-    sum.add(rr.y, rr.left_x, rr.right_x);
-    area += rr.right_x - rr.left_x + 1;
-    intervals[p] = make_int3(rr.y, rr.left_x, rr.right_x);
-    if (pass == 0) group_of_run[run] = (int)g;
-  }
-  const vsbs::Moments mo = sum.mean();
-  RunGroup out;
-  out.first = (int)i; out.count = (int)(p - i); out.tag = pass == 0 ? first.id : (int)key; out.slice = first.slice; out.area = area;
-  out.mean_x = mo.mean_x; out.mean_y = mo.mean_y; out.xx = mo.xx; out.xy = mo.xy; out.yy = mo.yy;
-  groups[g] = out;
+  head_pos[g] = i;
 }
 
-// tile_counts / tile_bases: ceil(n / 1024) words each; n_groups (device) receives the number of groups.  `groups` must
-// hold at least as many records as there are groups -- n is always enough.
+// One warp per group (grid-stride over the groups): the lanes fetch 32 runs of the group at a time -- the gather
+// through the sorted order is what costs -- and copy their intervals out; the moment sums then go through the 32 runs
+// in order, every lane running the same accumulator on shuffled values, so the float result is the sequential one.
+// pass 0 (components): tag = label of the runs, group_of_run[run] = index of its group.  pass 1 (result order): tag = key.
+__global__ void __launch_bounds__(256) group_runs_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ vals,
+                                                         unsigned n, const RunRec* __restrict__ runs,
+                                                         const unsigned* __restrict__ head_pos,
+                                                         const unsigned* __restrict__ n_groups_dev, int pass,
+                                                         RunGroup* __restrict__ groups, int* __restrict__ group_of_run,
+                                                         int3* __restrict__ intervals) {
+  const unsigned n_groups = *n_groups_dev;
+  const int lane = threadIdx.x & 31;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+    const unsigned begin = head_pos[g], end = g + 1 < n_groups ? head_pos[g + 1] : n;
+    vsbs::MomentSum sum;
+    int area = 0, label = 0, slice = 0;
+    for (unsigned base = begin; base < end; base += 32) {
+      const unsigned p = base + lane;
+      const int cnt = (int)min(32u, end - base);
+      int y = 0, lx = 0, rx = 0;
+      if (p < end) {
+        const unsigned run = vals[p];
+        const RunRec rr = runs[run];
+        y = rr.y; lx = rr.left_x; rx = rr.right_x;
+        intervals[p] = make_int3(y, lx, rx);
+        if (pass == 0) group_of_run[run] = (int)g;
+        if (p == begin) { label = rr.id; slice = rr.slice; }
+      }
+      for (int j = 0; j < cnt; ++j) {
+        const int yj = __shfl_sync(0xffffffffu, y, j), lj = __shfl_sync(0xffffffffu, lx, j), rj = __shfl_sync(0xffffffffu, rx, j);
+        sum.add(yj, lj, rj);
+        area += rj - lj + 1;
+      }
+    }
+    if (lane == 0) {
+      const vsbs::Moments mo = sum.mean();
+      RunGroup out;
+      out.first = (int)begin; out.count = (int)(end - begin); out.tag = pass == 0 ? label : (int)keys[begin]; out.slice = slice; out.area = area;
+      out.mean_x = mo.mean_x; out.mean_y = mo.mean_y; out.xx = mo.xx; out.xy = mo.xy; out.yy = mo.yy;
+      groups[g] = out;
+    }
+  }
+}
+
+// tile_counts / tile_bases: ceil(n / 1024) words each; head_pos: n words; n_groups (device) receives the number of
+// groups.  `groups` must hold at least as many records as there are groups -- n is always enough.
 int launch_group_runs(const unsigned* keys, const unsigned* vals, unsigned n, const RunRec* runs, int pass, unsigned* tile_counts,
-                      unsigned* tile_bases, unsigned* n_groups, RunGroup* groups, int* group_of_run, int3* intervals,
-                      cudaStream_t s) {
+                      unsigned* tile_bases, unsigned* head_pos, unsigned* n_groups, RunGroup* groups, int* group_of_run,
+                      int3* intervals, cudaStream_t s) {
   if (n == 0) { VSB_CUDA_OK(cudaMemsetAsync(n_groups, 0, sizeof(unsigned), s)); return 0; }
   const unsigned tiles = (n + kHeadTile - 1) / kHeadTile;
   group_heads_count_kernel<<<tiles, kHeadTile, 0, s>>>(keys, n, tile_counts);
   VSB_RC(launch_scan_u32(tile_counts, tile_bases, n_groups, (int)tiles, s));
-  group_runs_kernel<<<tiles, kHeadTile, 0, s>>>(keys, vals, n, runs, tile_bases, pass, groups, group_of_run, intervals);
+  group_heads_write_kernel<<<tiles, kHeadTile, 0, s>>>(keys, n, tile_bases, head_pos);
+  group_runs_kernel<<<148 * 8, 256, 0, s>>>(keys, vals, n, runs, head_pos, n_groups, pass, groups, group_of_run, intervals);
   VSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
