@@ -730,6 +730,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     if (R.frames.empty() || R.frames.back().first < c.slice) R.frames.emplace_back(c.slice, 0);
     R.frames.back().second += c.area;
   }
+  const double t_dbg2 = now_ms();
   // sizes / constraints of the representatives (GetCreateRegionInformation + size_adjust_map)
   {
     const int m = (int)regions.size();
@@ -750,6 +751,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     for (int i = 0; i < m; ++i) { regions[i]->size = info[i].x; regions[i]->constrained_id = info[i].y; }
     stats[7] += 1;
   }
+  const double t_dbg3 = now_ms();
   // ---------------- EnforceSpatialConnectedness (:666-904): tube decisions on the host over the components ----------------
   std::vector<int> label_of_group;                 // fresh label of every component that leaves its region; empty = no split
   if (o.enforce_spatial_connectedness) {
@@ -761,10 +763,17 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     std::vector<std::vector<vsbt::Tube>> all_tubes(num_regions);
     {
       const int nt = std::max(1, std::min<int>(host_threads, num_regions));
+      // regions with the most components first: the one that dominates must not be the last to start
+      std::vector<int> by_work(num_regions);
+      for (int r = 0; r < num_regions; ++r) by_work[r] = r;
+      std::stable_sort(by_work.begin(), by_work.end(), [&](int a, int b) { return regions[a]->pieces.size() > regions[b]->pieces.size(); });
       std::atomic<int> next_region{0};
       auto work = [&]() {
-        for (int r = next_region.fetch_add(1); r < num_regions; r = next_region.fetch_add(1))
+        for (int k = next_region.fetch_add(1); k < num_regions; k = next_region.fetch_add(1)) {
+          const int r = by_work[k];
+          if (regions[r]->pieces.size() < 2) continue;          // one component in one frame: nothing to split
           all_tubes[r] = vsbt::TubeSplitter(regions[r]->pieces, w, h, use_flow ? &flows : nullptr).run();
+        }
       };
       std::vector<std::thread> pool;
       for (int t = 1; t < nt; ++t) pool.emplace_back(work);
@@ -808,6 +817,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
       }
     }
   }
+  const double t_dbg4 = now_ms();
   // ---------------- result shaping, part 1 (dense_segmentation.cpp:335-398): which regions, which ids, which order ----------------
   const int overlap_start = slots - (flush_all ? 0 : overlap_frames);
   const int last_output_frame = std::min(slots - 1, overlap_start);
@@ -846,6 +856,10 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
     ENG_CUDA(cudaStreamSynchronize(stream));        // the tables are stack vectors
   }
   stats[5] += now_ms() - t_host0;
+  if (stage_debug)
+    fprintf(stderr, "[vsb200 stage] host: regions from components %.2f ms, sizes %.2f ms, tubes %.2f ms (%d regions, %d threads), ids + order + tables %.2f ms\n",
+            t_dbg2 - t_host0, t_dbg3 - t_dbg2, t_dbg4 - t_dbg3, (int)regions.size(), host_threads, now_ms() - t_dbg4);
+  const double t_dbg5 = now_ms();
   // split-off tubes get their fresh labels in the label volume (:866-893), then every run its place in the result:
   // (frame, rank of its region), stable, so that a region's intervals stay in raster order; K10 over that order gives the
   // ShapeMoments of every region in every frame and the interval arrays of the output, ready to copy
@@ -894,6 +908,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   d2h_bytes += 8.0 * n_pairs + 8.0 * regions.size() + (double)sizeof(RunGroup) * n_slices_out + (double)sizeof(int3) * n_runs;
   stats[7] += 3;
   const double t_host1 = now_ms();
+  if (stage_debug) fprintf(stderr, "[vsb200 stage] result order + neighbour pairs on the device, copies out: %.2f ms (%llu pairs)\n", t_host1 - t_dbg5, n_pairs);
   for (unsigned long long key : pairs) {
     const int la = (int)(key >> 32), lb = (int)(key & 0xffffffffu);
     auto ia = label2region.find(la), ib = label2region.find(lb);
@@ -1017,6 +1032,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   }
   ++chunk_id;
   stats[5] += now_ms() - t_host1;
+  if (stage_debug) fprintf(stderr, "[vsb200 stage] host: neighbour lists + frames of the result %.2f ms\n", now_ms() - t_host1);
   float ms;
   cudaEventElapsedTime(&ms, ev[0], ev[1]); stats[2] += ms;
   cudaEventElapsedTime(&ms, ev[1], ev[2]); stats[3] += ms;

@@ -35,6 +35,7 @@ struct TubeSlice {
   int frame = -1;
   std::vector<int> pieces;          // indices into the region's piece list, ascending (= raster order of their first interval)
   Shape shape;
+  std::vector<Interval> merged;     // scan intervals of a slice made of several pieces, in raster order (empty for one piece)
 };
 typedef std::vector<TubeSlice> Tube;
 
@@ -118,36 +119,49 @@ class TubeSplitter {
     return (int)best_idx;
   }
 
-  // Shape of the union of several pieces of one frame: their intervals in raster order through one accumulator.
-  Shape union_shape(const std::vector<int>& pieces) const {
-    std::vector<Interval> all;
-    for (int p : pieces) all.insert(all.end(), pieces_[p].intervals, pieces_[p].intervals + pieces_[p].n_intervals);
-    std::sort(all.begin(), all.end(), [](const Interval& a, const Interval& b) { return a.y != b.y ? a.y < b.y : a.lx < b.lx; });
+  // Scan intervals of a slice in raster order: the piece's own view, or the merged list of a slice of several pieces.
+  void intervals_of(const TubeSlice& s, const Interval** first, size_t* n) const {
+    if (s.pieces.size() == 1) { *first = pieces_[s.pieces[0]].intervals; *n = (size_t)pieces_[s.pieces[0]].n_intervals; }
+    else { *first = s.merged.data(); *n = s.merged.size(); }
+  }
+
+  // Union of two slices of one frame: one linear merge of their interval lists (raster order), the moments of the union
+  // through one accumulator over the merged list.
+  void unite(const TubeSlice& a, const TubeSlice& b, TubeSlice* out) const {
+    out->frame = a.frame;
+    out->pieces.resize(a.pieces.size() + b.pieces.size());
+    std::merge(a.pieces.begin(), a.pieces.end(), b.pieces.begin(), b.pieces.end(), out->pieces.begin());
+    const Interval *pa, *pb;
+    size_t na, nb;
+    intervals_of(a, &pa, &na);
+    intervals_of(b, &pb, &nb);
+    out->merged.resize(na + nb);
+    std::merge(pa, pa + na, pb, pb + nb, out->merged.begin(),
+               [](const Interval& p, const Interval& q) { return p.y != q.y ? p.y < q.y : p.lx < q.lx; });
     vsbs::MomentSum sum;
-    for (const Interval& iv : all) sum.add(iv.y, iv.lx, iv.rx);
-    return vsbs::shape_from_moments(sum.mean());
+    for (const Interval& iv : out->merged) sum.add(iv.y, iv.lx, iv.rx);
+    out->shape = vsbs::shape_from_moments(sum.mean());
   }
 
   // `from` folded into `into` (into's slices first where both have one for a frame; the union's shape is recomputed).
-  void fold(const Tube& into, const Tube& from, Tube* out) const {
-    if (into.empty()) { *out = from; return; }
-    if (from.empty()) { *out = into; return; }
+  // Both tubes are consumed: the caller replaces one with the result and drops the other.
+  void fold(Tube& into, Tube& from, Tube* out) const {
+    if (into.empty()) { out->swap(from); return; }
+    if (from.empty()) { out->swap(into); return; }
+    out->reserve(into.size() + from.size());
     size_t i = 0, j = 0;
     while (i < into.size() && j < from.size()) {
-      if (into[i].frame < from[j].frame) out->push_back(into[i++]);
-      else if (into[i].frame > from[j].frame) out->push_back(from[j++]);
+      if (into[i].frame < from[j].frame) out->push_back(std::move(into[i++]));
+      else if (into[i].frame > from[j].frame) out->push_back(std::move(from[j++]));
       else {
         TubeSlice both;
-        both.frame = into[i].frame;
-        both.pieces.resize(into[i].pieces.size() + from[j].pieces.size());
-        std::merge(into[i].pieces.begin(), into[i].pieces.end(), from[j].pieces.begin(), from[j].pieces.end(), both.pieces.begin());
-        both.shape = union_shape(both.pieces);
+        unite(into[i], from[j], &both);
         out->push_back(std::move(both));
         ++i; ++j;
       }
     }
-    out->insert(out->end(), into.begin() + i, into.end());
-    out->insert(out->end(), from.begin() + j, from.end());
+    for (; i < into.size(); ++i) out->push_back(std::move(into[i]));
+    for (; j < from.size(); ++j) out->push_back(std::move(from[j]));
   }
 
   // Calls visit(slice_a, slice_b) for every frame both tubes have; returns the number of such frames.
