@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hierarchy", action="store_true",
+                    help="N = 1 only: add a leg that runs the whole of config 3 -- dense over-segmentation feeding the hierarchical "
+                         "region stage (RegionSegmentationUnit, defaults) -- and report it under \"hierarchy\"")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -342,6 +345,40 @@ def main():
         "ms_per_step_series": leg_dev["series"], "regions_per_step": leg_dev["regions"],
         "per_rank": leg_dev["per_rank"],
     }
+    if rank == 0 and world == 1 and args.hierarchy:
+        # config 3 end to end: host frames -> DenseSegmentationUnit -> RegionSegmentationUnit (segmentation tree), flushed
+        from video_segment_b200.unit import RegionSegmentationUnit
+        dense = DenseSegmentationUnit(device=local_rank)
+        region = RegionSegmentationUnit(raw_records=True)
+        assert dense.open_streams(w, h) and region.open_streams(w, h)
+        n_in = 1 + FRAMES_PER_STEP * (W + K)
+        fed, out, t_region, levels = 0, 0, 0.0, 0
+        def feed(results):
+            nonlocal fed, out, t_region, levels
+            for r in results:
+                t1 = time.perf_counter()
+                recs = region.process_frame(r, pinned[frame_index(fed)].numpy())
+                t_region += time.perf_counter() - t1
+                fed += 1
+                out += len(recs)
+                for rec in recs:
+                    levels = max(levels, int(rec[7]))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for kf in range(n_in):
+            feed(dense.process_frame(pinned[frame_index(kf)].numpy()))
+        feed(dense.post_process())
+        t1 = time.perf_counter()
+        out += len(region.post_process())
+        t_region += time.perf_counter() - t1
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        line["hierarchy"] = {"value": out / dt, "unit": "frames/s", "frames": out, "seconds": round(dt, 2),
+                             "region_stage_ms_per_frame": round(1000.0 * t_region / max(out, 1), 2),
+                             "region_stage_share": round(t_region / dt, 3), "hierarchy_levels": levels,
+                             "what": "config 3 whole: dense over-segmentation + hierarchical region stage (RegionSegmentationOptions "
+                                     "defaults: chunk sets of 6 chunks, overlap 2, appearance descriptor), host frames in, records out, flushed"}
+        dense.close(); region.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind, make, cores = cpu_engine()
         nfr = 1 + 2 * FRAMES_PER_STEP      # the free first chunk and one constrained chunk: ~20-30 s of CPU work at 1080p

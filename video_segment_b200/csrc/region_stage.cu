@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <limits>
 #include <memory>
@@ -299,7 +300,11 @@ struct Device {                                // per handle
   DistJob* d_jobs = nullptr; DistJob* h_jobs = nullptr; float* d_dist = nullptr; float* h_dist = nullptr; size_t jobs_cap = 0;
   double kernel_ms = 0;
   long long launches = 0;
+  // development taps (VSB200_STAGE_DEBUG): wall-clock ms since the last chunk-set boundary
+  double t_add_frame = 0, t_evaluate = 0, t_hierarchy = 0, t_retrieve = 0, t_push = 0, t_begin = 0;
+  long long n_evaluate = 0, n_jobs = 0, n_merge_launches = 0;
 };
+inline double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // The regions of one chunk set and everything computed over them (the hierarchical half of Segmentation).
 class ChunkSet {
@@ -354,6 +359,7 @@ class ChunkSet {
   // AddOverSegmentation (segmentation.cpp:200-239): rasters on the host, descriptors on the device.  d_ids is scratch;
   // the frame (and flow) are already resident.
   int add_frame(const vsb200_frame_result& r, bool flow_valid) {
+    const double t_in = wall_ms();
     Level& base = levels_[0];
     size_t n_runs = 0;
     for (int k = 0; k < r.n_regions; ++k) n_runs += (size_t)(r.interval_offset[k + 1] - r.interval_offset[k]);
@@ -392,6 +398,7 @@ class ChunkSet {
     RS_CUDA(cudaStreamSynchronize(s));          // h_runs / the frame staging buffers are reused by the next frame
     dev_->launches += 3;
     ++frame_number_;
+    dev_->t_add_frame += wall_ms() - t_in;
     return 0;
   }
 
@@ -496,6 +503,8 @@ int ChunkSet::finish_descriptors() {
 int ChunkSet::evaluate(const std::vector<DistJob>& jobs, float inv_av, std::vector<float>* out) {
   out->resize(jobs.size());
   if (jobs.empty()) return 0;
+  const double t_in = wall_ms();
+  ++dev_->n_evaluate; dev_->n_jobs += (long long)jobs.size();
   if (jobs.size() > dev_->jobs_cap) {
     if (dev_->d_jobs) cudaFree(dev_->d_jobs);
     if (dev_->d_dist) cudaFree(dev_->d_dist);
@@ -518,6 +527,7 @@ int ChunkSet::evaluate(const std::vector<DistJob>& jobs, float inv_av, std::vect
   RS_CUDA(cudaStreamSynchronize(s));
   memcpy(out->data(), dev_->h_dist, jobs.size() * sizeof(float));
   ++dev_->launches;
+  dev_->t_evaluate += wall_ms() - t_in;
   return 0;
 }
 
@@ -525,6 +535,7 @@ int ChunkSet::merge_slots(int a, int b, int dst) {
   merge_slots_kernel<<<1, 256, 0, dev_->stream>>>(slots_, weight_sum_, num_vectors_, a, b, dst, B_, set_frames_, opt_.flow_bins, slot_words_);
   RS_CUDA(cudaGetLastError());
   ++dev_->launches;
+  ++dev_->n_merge_launches;
   return 0;
 }
 
@@ -998,7 +1009,10 @@ struct vsb200_region {
   }
 
   int segment_and_output(int overlap_start_, int lookahead_start_) {   // SegmentAndOutputChunk (:313-365)
+    const double t_h0 = wall_ms();
     RS_RC(seg->run_hierarchy());
+    dev.t_hierarchy += wall_ms() - t_h0;
+    const double t_r0 = wall_ms();
     const int computed = seg->levels();
     if (computed > (int)max_region_ids.size()) max_region_ids.resize(computed, 0);
     seg->constrain_to_interval(0, lookahead_start_);
@@ -1019,6 +1033,12 @@ struct vsb200_region {
       ++num_output_frames;
     }
     ++chunk_sets;
+    dev.t_retrieve += wall_ms() - t_r0;
+    if (getenv("VSB200_STAGE_DEBUG"))
+      fprintf(stderr, "[vsb200 region] chunk set %d: %d frames, %d levels; add_frame %.1f ms, hierarchy %.1f ms (distance batches %lld with %lld pairs: %.1f ms; slot merges %lld), ids + records %.1f ms; begin_chunk %.1f ms; all pushes so far %.1f ms\n",
+              chunk_sets - 1, seg->frames(), seg->levels(), dev.t_add_frame, dev.t_hierarchy, dev.n_evaluate, dev.n_jobs, dev.t_evaluate, dev.n_merge_launches, dev.t_retrieve, dev.t_begin, dev.t_push + (wall_ms() - t_h0));
+    dev.t_add_frame = dev.t_evaluate = dev.t_hierarchy = dev.t_retrieve = dev.t_begin = 0;
+    dev.n_evaluate = dev.n_jobs = dev.n_merge_launches = 0;
     return 0;
   }
 
@@ -1085,6 +1105,8 @@ int vsb200_region_push(vsb200_region* r, const vsb200_frame_result* overseg, con
   if (r->flushed) { set_error("region_push after flush"); return VSB200_ERR_INVALID; }
   if (overseg->width != r->w || overseg->height != r->h) { set_error("region_push: over-segmentation of another frame size"); return VSB200_ERR_INVALID; }
   RS_CUDA(cudaSetDevice(r->device));
+  const double t_push0 = wall_ms();
+  struct PushTimer { Device& d; double t0; ~PushTimer() { d.t_push += wall_ms() - t0; } } push_timer{r->dev, t_push0};
   const size_t before = r->ready.size();
   const Options& o = r->opt;
   if (!r->seg) r->seg.reset(new ChunkSet(o, r->w, r->h, r->chunk_sets, &r->dev));
@@ -1106,15 +1128,17 @@ int vsb200_region_push(vsb200_region* r, const vsb200_frame_result* overseg, con
     if (!r->new_seg) r->new_seg.reset(new ChunkSet(o, r->w, r->h, r->chunk_sets + 1, &r->dev));
     if (r->overlap_start < 0) r->overlap_start = r->seg->frames();
     if (boundary) {
+      const double tb = wall_ms();
       std::unordered_map<int, Node*> mapping;
       std::unordered_map<int, Node*>* mp = (r->read_chunks % o.chunk_set_size < lookahead_start_chunk) ? &mapping : nullptr;
       RS_RC(r->seg->begin_chunk(*overseg, nullptr, mp));
       RS_RC(r->new_seg->begin_chunk(*overseg, mp, nullptr));
+      r->dev.t_begin += wall_ms() - tb;
     }
     RS_RC(r->seg->add_frame(*overseg, flow_valid));
     RS_RC(r->new_seg->add_frame(*overseg, flow_valid));
   } else {
-    if (boundary) RS_RC(r->seg->begin_chunk(*overseg, nullptr, nullptr));
+    if (boundary) { const double tb = wall_ms(); RS_RC(r->seg->begin_chunk(*overseg, nullptr, nullptr)); r->dev.t_begin += wall_ms() - tb; }
     RS_RC(r->seg->add_frame(*overseg, flow_valid));
   }
   if (r->read_chunks % o.chunk_set_size >= lookahead_start_chunk && r->lookahead_start < 0) r->lookahead_start = r->seg->frames();
