@@ -187,29 +187,39 @@ __global__ void __launch_bounds__(256) merge_slots_kernel(float* __restrict__ sl
 struct DistJob { int slot_a, slot_b, size_a, size_b; };
 
 // RegionInformation::DescriptorDistances + SquaredORDistance[SizePenalized]::Evaluate (region_descriptor.h:195-230) for a
-// list of region pairs, one warp per pair: ColorHistogram::ChiSquareDist (histograms.cpp:391-407), FlowDescriptor::
-// RegionDistance (region_descriptor.cpp:465-498), RegionSizePenalizer::RegionDistance (:377-383).
-__global__ void __launch_bounds__(256) slot_distance_kernel(const float* __restrict__ slots, const int* __restrict__ num_vectors,
-                                                            const DistJob* __restrict__ jobs, int n_jobs, int B, int frames, int bins,
-                                                            size_t slot_words, int use_appearance, int use_flow, int use_size,
-                                                            float penalizer, float inv_av_region_size, float* __restrict__ out) {
-  const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  const unsigned lane = threadIdx.x & 31u;
-  if (warp >= n_jobs) return;
-  const DistJob j = jobs[warp];
+// list of region pairs, one CTA per pair: ColorHistogram::ChiSquareDist (histograms.cpp:391-407) over all four warps,
+// FlowDescriptor::RegionDistance (region_descriptor.cpp:465-498) on warp 0, RegionSizePenalizer::RegionDistance
+// (:377-383).  `jobs` and `out` are mapped pinned host memory: a greedy merge costs one launch and one stream
+// synchronisation, no copies (a batch is ~170 pairs: 3 KB in, 700 B out over PCIe from inside the kernel).
+constexpr int kDistThreads = 128;
+__global__ void __launch_bounds__(kDistThreads) slot_distance_kernel(const float* __restrict__ slots, const int* __restrict__ num_vectors,
+                                                                     const DistJob* __restrict__ jobs, int n_jobs, int B, int frames, int bins,
+                                                                     size_t slot_words, int use_appearance, int use_flow, int use_size,
+                                                                     float penalizer, float inv_av_region_size, float* __restrict__ out) {
+  __shared__ DistJob job;
+  __shared__ double part[kDistThreads / 32];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) job = jobs[blockIdx.x];
+  __syncthreads();
+  const DistJob j = job;
   const float* A = slots + (size_t)j.slot_a * slot_words;
   const float* Bs = slots + (size_t)j.slot_b * slot_words;
   float result = 1.0f;
   if (use_appearance) {
     double sum = 0.0;
-    for (int k = (int)lane; k < B; k += 32) {
+    for (int k = (int)threadIdx.x; k < B; k += kDistThreads) {
       const float a = __ldg(&A[k]), c = __ldg(&Bs[k]);
       const float add = a + c;
       if (fabs((double)add) > 1e-12) { const float sub = a - c; sum += (double)(sub * sub / add); }
     }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    result *= (1.0f - (float)(0.5 * sum));
+    if (lane == 0) part[warp] = sum;
+    __syncthreads();
+    double total = 0.0;
+    for (int k = 0; k < kDistThreads / 32; ++k) total += part[k];
+    result *= (1.0f - (float)(0.5 * total));
   }
+  if (warp != 0) return;
   if (use_flow) {
     double sum = 0, sum_w = 0;
     for (int t = (int)lane; t < frames; t += 32) {
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(256) slot_distance_kernel(const float* __restr
       const float size_scale = (float)(1.0 + (double)penalizer * log((double)((float)min_sz * inv_av_region_size)) / log(2.0));
       d = fmaxf(0.f, fminf(1.f, d * fminf(1.0f, size_scale)));
     }
-    out[warp] = d;
+    out[blockIdx.x] = d;
   }
 }
 
@@ -506,24 +516,22 @@ int ChunkSet::evaluate(const std::vector<DistJob>& jobs, float inv_av, std::vect
   const double t_in = wall_ms();
   ++dev_->n_evaluate; dev_->n_jobs += (long long)jobs.size();
   if (jobs.size() > dev_->jobs_cap) {
-    if (dev_->d_jobs) cudaFree(dev_->d_jobs);
-    if (dev_->d_dist) cudaFree(dev_->d_dist);
     if (dev_->h_jobs) cudaFreeHost(dev_->h_jobs);
     if (dev_->h_dist) cudaFreeHost(dev_->h_dist);
-    dev_->jobs_cap = jobs.size() * 2 + 1024;
-    RS_CUDA(cudaMalloc(&dev_->d_jobs, dev_->jobs_cap * sizeof(DistJob)));
-    RS_CUDA(cudaMalloc(&dev_->d_dist, dev_->jobs_cap * sizeof(float)));
-    RS_CUDA(cudaMallocHost(&dev_->h_jobs, dev_->jobs_cap * sizeof(DistJob)));
-    RS_CUDA(cudaMallocHost(&dev_->h_dist, dev_->jobs_cap * sizeof(float)));
+    dev_->h_jobs = nullptr; dev_->h_dist = nullptr; dev_->jobs_cap = 0;
+    const size_t cap = jobs.size() * 2 + 1024;
+    RS_CUDA(cudaHostAlloc(&dev_->h_jobs, cap * sizeof(DistJob), cudaHostAllocMapped));
+    RS_CUDA(cudaHostAlloc(&dev_->h_dist, cap * sizeof(float), cudaHostAllocMapped));
+    RS_CUDA(cudaHostGetDevicePointer((void**)&dev_->d_jobs, dev_->h_jobs, 0));
+    RS_CUDA(cudaHostGetDevicePointer((void**)&dev_->d_dist, dev_->h_dist, 0));
+    dev_->jobs_cap = cap;
   }
   memcpy(dev_->h_jobs, jobs.data(), jobs.size() * sizeof(DistJob));
   cudaStream_t s = dev_->stream;
-  RS_CUDA(cudaMemcpyAsync(dev_->d_jobs, dev_->h_jobs, jobs.size() * sizeof(DistJob), cudaMemcpyHostToDevice, s));
-  slot_distance_kernel<<<(unsigned)((jobs.size() * 32 + 255) / 256), 256, 0, s>>>(
+  slot_distance_kernel<<<(unsigned)jobs.size(), kDistThreads, 0, s>>>(
       slots_, num_vectors_, dev_->d_jobs, (int)jobs.size(), B_, set_frames_, opt_.flow_bins, slot_words_, opt_.use_appearance ? 1 : 0,
       opt_.use_flow ? 1 : 0, opt_.use_size_penalizer ? 1 : 0, opt_.small_region_penalizer, inv_av, dev_->d_dist);
   RS_CUDA(cudaGetLastError());
-  RS_CUDA(cudaMemcpyAsync(dev_->h_dist, dev_->d_dist, jobs.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
   RS_CUDA(cudaStreamSynchronize(s));
   memcpy(out->data(), dev_->h_dist, jobs.size() * sizeof(float));
   ++dev_->launches;
@@ -1003,7 +1011,7 @@ struct vsb200_region {
     seg.reset(); new_seg.reset();
     auto F = [](void* p) { if (p) cudaFree(p); };
     auto FH = [](void* p) { if (p) cudaFreeHost(p); };
-    F(dev.d_bgr); F(dev.d_flow); F(dev.d_ids); F(dev.d_runs); F(dev.d_jobs); F(dev.d_dist);
+    F(dev.d_bgr); F(dev.d_flow); F(dev.d_ids); F(dev.d_runs);      // d_jobs / d_dist alias the mapped host buffers
     FH(dev.h_bgr); FH(dev.h_flow); FH(dev.h_runs); FH(dev.h_jobs); FH(dev.h_dist);
     if (dev.stream) cudaStreamDestroy(dev.stream);
   }
