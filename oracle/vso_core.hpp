@@ -107,6 +107,8 @@ class DenseGraph {
   void DetermineNeighborIds(RegionInfoList* list, RegionInfoPtrMap* map); // segmentation_graph.h:466-496
 
   int num_frames() const { return num_frames_; }
+  // test hook: a graph of `frames` slices whose union-find is the given label volume (no edges), ready for ObtainResults
+  void TestLoadLabels(const int32_t* labels, int frames);
   // debug taps
   std::vector<int32_t> node_labels_after_flatten;   // [num_frames * N]
   std::vector<int32_t> id_images_after_n4;          // [num_frames * N], -1 on virtual slices

@@ -951,4 +951,44 @@ void DenseGraph::EnforceSpatialConnectedness(RegionInfoList* region_list, Region
   }
 }
 
+// Test hook (tests/host_tubes_check.cpp): the state SegmentFullGraph would leave behind for a given label volume -- every
+// voxel's parent is the first voxel of its label -- so that ObtainResults / EnforceSpatialConnectedness can be run on
+// label volumes made up by a test.
+void DenseGraph::TestLoadLabels(const int32_t* labels, int frames) {
+  std::vector<float> blank((size_t)w_ * h_ * 3, 0.f);
+  std::unordered_map<int, int> first_of_label;
+  for (int t = 0; t < frames; ++t) {
+    AddNodesWithDescriptors(blank.data(), nullptr);
+    ++num_frames_;
+  }
+  const int n = w_ * h_ * frames;
+  for (int i = 0; i < n; ++i) {
+    auto it = first_of_label.find(labels[i]);
+    if (it == first_of_label.end()) { first_of_label[labels[i]] = i; continue; }
+    regions_[i].my_id = it->second;
+    regions_[it->second].sz += 1;
+  }
+}
+
 }  // namespace vso
+
+// region index (position in the region list after EnforceSpatialConnectedness) of every voxel of a label volume;
+// flows: [frames][h][w][2] backward flow or NULL.  Returns the number of regions.
+extern "C" int vso_test_spatial_connectedness(const int32_t* labels, int w, int h, int frames, const float* flows,
+                                              int32_t* region_index_out) {
+  vso::DenseGraph g(w, h, frames, false, false);
+  g.TestLoadLabels(labels, frames);
+  vso::RegionInfoList list;
+  vso::RegionInfoPtrMap map;
+  std::vector<const float*> fl;
+  if (flows) for (int t = 0; t < frames; ++t) fl.push_back(t == 0 ? nullptr : flows + (size_t)t * w * h * 2);
+  g.ObtainResults(&list, &map, flows ? &fl : nullptr, false, true);
+  std::fill(region_index_out, region_index_out + (size_t)w * h * frames, -1);
+  for (const auto& ri : list) {
+    if (!ri->raster) continue;
+    for (const auto& slice : *ri->raster)
+      for (const auto& s : *slice.second)
+        for (int x = s.left_x; x <= s.right_x; ++x) region_index_out[((size_t)slice.first * h + s.y) * w + x] = ri->index;
+  }
+  return (int)list.size();
+}

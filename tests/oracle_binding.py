@@ -79,6 +79,19 @@ def build_oracle(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def host_tubes_check(seed: int, n_cases: int, with_flow: bool):
+    """(#mismatching volumes, first mismatch or a summary) of the product's tube split (csrc/tubes.hpp) against the
+    oracle's EnforceSpatialConnectedness on random label volumes (tests/host_tubes_check.cpp, oracle/libtubes_check.so)."""
+    path = os.path.join(_ROOT, "oracle", "libtubes_check.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "libvso.so", "libtubes_check.so"])
+    L = C.CDLL(path)
+    L.host_tubes_check.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    msg = C.create_string_buffer(400)
+    bad = L.host_tubes_check(seed, n_cases, int(with_flow), msg, 400)
+    return bad, msg.value.decode()
+
+
 _lib = None
 
 

@@ -480,3 +480,14 @@ def test_oracle_equals_compiled_reference_on_random_cases(block):
         ref = rc.run_stream(rb.ReferenceDense, clip, flows, opts)
         mine = rc.run_stream(ob.OracleDense, clip, flows, opts)
         assert rc.first_difference(ref, mine) is None, (seed, clip.shape, opts)
+
+
+@pytest.mark.parametrize("seed,with_flow", [(1, False), (2, False), (3, True), (4, True)])
+def test_product_tube_split_equals_oracle(seed, with_flow):
+    """video_segment_b200/csrc/tubes.hpp (the host half of EnforceSpatialConnectedness: tube matching, folds, joins, on
+    the moment accumulator of csrc/shape_math.hpp) against the oracle's restatement of dense_segmentation_graph.h:666-904
+    on random label volumes (moving blobs that break apart and rejoin, specks), with and without flow: the same
+    regions in the same order on every volume."""
+    bad, msg = ob.host_tubes_check(seed, 200, with_flow)
+    assert bad == 0, msg
+    assert "regions split" in msg and int(msg.split(",")[1].split()[0]) > 100, msg      # the volumes do exercise the split
