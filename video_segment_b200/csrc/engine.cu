@@ -643,8 +643,6 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
               c[32] / 1e6, c[33] / 1e6, c[34] / 1e6, c[35] / 1e6, c[36] / 1e6, c[37] / 1e6);
       fprintf(f, "hub_not_frozen reasons: same_id_or_hubs3 %llu con_conflict %llu open_hubs3 %llu bound %llu\n", c[8], c[9], c[10], c[11]);
       fprintf(f, "scans: event thread Mcycles %.1f, total %.1f (staging+sort %.1f, sub-cluster replay %.1f); staged roots %llu, events %llu of %llu edges: absorb %llu big-big %llu generic+speculated %llu, hub swaps %llu; speculated meetings %llu, scans redone %llu\n", c[42] / 1e6, c[43] / 1e6, c[45] / 1e6, c[46] / 1e6, c[44], c[47], c[48], c[49], c[50], c[51], c[52], c[53], c[54]);
-      fprintf(f, "event replay Mcycles by kind: absorb %.1f big-big %.1f generic %.1f speculated %.1f, batch fetch %.1f\n",
-              c[22] / 1e6, c[23] / 1e6, c[24] / 1e6, c[25] / 1e6, c[26] / 1e6);
       fclose(f);
     }
   }

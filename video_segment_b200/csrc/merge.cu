@@ -846,10 +846,7 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
     RegionRec H;
     H.sz = 0; H.con = -1; H.d0 = H.d1 = H.d2 = 0.f; H.fin = 0; H.pad0 = H.pad1 = 0;
     unsigned long long n_abs = 0, n_bb = 0, n_gen = 0, n_swap = 0;
-    long long cyc_kind[4] = {0, 0, 0, 0}, cyc_fetch = 0;     // development taps (p.debug only)
     for (int e0 = 0; e0 < n_ev; e0 += 32) {
-      long long tb0 = 0;
-      if (p.debug) tb0 = clock64();
       const int cnt = min(32, n_ev - e0);
       int my_i = 0, my_kind = 0, my_a = 0, my_b = 0, my_sz = 0, my_fin = 0;      // kind: 0 absorb, 1 big-big, 2 generic
       float my_d0 = 0.f, my_d1 = 0.f, my_d2 = 0.f;
@@ -866,10 +863,7 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
           } else my_kind = 1;
         }
       }
-      if (p.debug) cyc_fetch += clock64() - tb0;
       for (int t = 0; t < cnt; ++t) {
-        long long te0 = 0;
-        if (p.debug) te0 = clock64();
         const int kind = __shfl_sync(0xffffffffu, my_kind, t);
         const int ea_ = __shfl_sync(0xffffffffu, my_a, t), eb_ = __shfl_sync(0xffffffffu, my_b, t);
         if (kind == 0) {
@@ -898,7 +892,6 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
           H.sz += xsz;
           if (lane == 0) C.par[eb_] = (unsigned short)h;
           ++n_abs;
-          if (p.debug) cyc_kind[0] += clock64() - te0;
           continue;
         }
         // big-big / generic / speculated meetings: lane 0 with the full decision tree, on the records in shared memory
@@ -922,7 +915,6 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
           }
           fail = __shfl_sync(0xffffffffu, fail, 0);
           ++n_gen;
-          if (p.debug) cyc_kind[3] += clock64() - te0;
           if (fail) { e0 = n_ev; break; }
           continue;
         }
@@ -943,7 +935,6 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
         }
         __syncwarp();
         if (kind == 1) ++n_bb; else ++n_gen;
-        if (p.debug) cyc_kind[kind] += clock64() - te0;
       }
     }
     if (cur >= 0 && lane == 0) scan_store(C.rec, cur, H);
@@ -951,9 +942,6 @@ __device__ void split_scan(const MergeParams& p, MergeShared& S, const int b, co
       t3 = clock64();
       atomicAdd(&p.debug[kNumBuckets * 4 + 57], n_abs); atomicAdd(&p.debug[kNumBuckets * 4 + 58], n_bb);
       atomicAdd(&p.debug[kNumBuckets * 4 + 59], n_gen); atomicAdd(&p.debug[kNumBuckets * 4 + 60], n_swap);
-      atomicAdd(&p.debug[kNumBuckets * 4 + 30], (unsigned long long)cyc_kind[0]); atomicAdd(&p.debug[kNumBuckets * 4 + 31], (unsigned long long)cyc_kind[1]);
-      atomicAdd(&p.debug[kNumBuckets * 4 + 32], (unsigned long long)cyc_kind[2]); atomicAdd(&p.debug[kNumBuckets * 4 + 33], (unsigned long long)cyc_kind[3]);
-      atomicAdd(&p.debug[kNumBuckets * 4 + 34], (unsigned long long)cyc_fetch);
     }
   }
   __syncthreads();
