@@ -55,22 +55,26 @@ def edge_build_bytes(w, h):
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.indices, self.rows, self.stop_flag = set(indices), [], False
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        # ONE sampler per job (rank 0), one query for all GPUs of the job: eight ranks polling nvidia-smi next to each
+        # other serialise on the driver and show up in everybody's step time
+        q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                for line in out.splitlines():
+                    f = [x.strip() for x in line.split(",")]
+                    if f and f[0].isdigit() and int(f[0]) in self.indices:
+                        self.rows.append(f[1:])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def summary(self):
         if not self.rows:
@@ -259,9 +263,12 @@ def main():
         seam_exchange(unit, have_first)  # warm-up of the exchange too (NCCL opens its peer channels on first use)
         st0, io0 = unit.stats(), unit.io_stats()
         link0 = link.stats() if link else None
-        sampler = ClockSampler(local_rank)
+        visible = [int(x) for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip().isdigit()]
+        gpu_ids = [visible[i] if i < len(visible) else i for i in range(world)]      # physical indices of local ranks 0 .. world-1
+        sampler = ClockSampler(gpu_ids) if rank == 0 else None
         barrier()
-        sampler.start()
+        if sampler:
+            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
@@ -282,7 +289,8 @@ def main():
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
-        sampler.stop_flag = True
+        if sampler:
+            sampler.stop_flag = True
         ms = e0.elapsed_time(e1)
         st1, io1 = unit.stats(), unit.io_stats()
         link1 = link.stats() if link else None
@@ -300,7 +308,7 @@ def main():
             gathered = [None] * world
             dist.all_gather_object(gathered, mine)
             per_rank = gathered
-        return dict(ms=float(t.item()), wall=wall, frames=timed, stats=d, io=dio, clocks=sampler.summary(), series=series,
+        return dict(ms=float(t.item()), wall=wall, frames=timed, stats=d, io=dio, clocks=sampler.summary() if sampler else None, series=series,
                     regions=regions, per_rank=per_rank)
 
     leg_dev = run_leg(True)
