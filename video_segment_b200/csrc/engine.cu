@@ -132,6 +132,7 @@ struct vsb200_dense {
   int segment_and_output(bool flush_all, std::vector<std::unique_ptr<FrameOut>>* results);
   int merge_constrained_regions(int slots);
   int upload_id_map(const FrameOut& f, int* dst);
+  int ensure_tmp_capacity(size_t n_regions);
   int ensure_shape_capacity(size_t n_runs);
   int ensure_host_groups(int which, size_t n_groups, size_t n_runs);
 };
@@ -223,13 +224,31 @@ int vsb200_dense::init() {
   return 0;
 }
 
+// Per-region scratch (ids in, records out), sized by the number of regions of the chunk.
+int vsb200_dense::ensure_tmp_capacity(size_t n_regions) {
+  if (n_regions <= tmp_cap) return 0;
+  if (d_tmp_ids) cudaFree(d_tmp_ids);
+  if (d_tmp_info) cudaFree(d_tmp_info);
+  d_tmp_ids = nullptr; d_tmp_info = nullptr; tmp_cap = 0;
+  const size_t cap = n_regions * 2 + 1024;
+  ENG_CUDA(cudaMalloc(&d_tmp_ids, cap * 2 * sizeof(int)));
+  ENG_CUDA(cudaMalloc(&d_tmp_info, cap * sizeof(RegionRec)));
+  tmp_cap = cap;
+  return 0;
+}
+
 // Device buffers of the shape stage, sized by the number of scan intervals of the chunk.
 int vsb200_dense::ensure_shape_capacity(size_t n_runs) {
   if (n_runs <= shape_cap) return 0;
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_cc_parent); F(d_group_of_run); F(d_group_tab); F(d_shist); F(d_head_pos); F(d_tile_counts); F(d_tile_bases); F(d_ngroups);
-  for (int k = 0; k < 2; ++k) { F(d_skeys[k]); F(d_svals[k]); F(d_groups[k]); F(d_intervals[k]); }
-  shape_cap = 0;
+  d_cc_parent = d_group_of_run = d_group_tab = nullptr;
+  d_shist = d_head_pos = d_tile_counts = d_tile_bases = d_ngroups = nullptr;
+  for (int k = 0; k < 2; ++k) {
+    F(d_skeys[k]); F(d_svals[k]); F(d_groups[k]); F(d_intervals[k]);
+    d_skeys[k] = d_svals[k] = nullptr; d_groups[k] = nullptr; d_intervals[k] = nullptr;
+  }
+  shape_cap = 0;                                 // a failed allocation below leaves a consistent (empty) state behind
   const size_t cap = n_runs + n_runs / 2 + 4096;
   ENG_CUDA(cudaMalloc(&d_cc_parent, cap * sizeof(int)));
   ENG_CUDA(cudaMalloc(&d_group_of_run, cap * sizeof(int)));
@@ -469,13 +488,7 @@ int vsb200_dense::merge_constrained_regions(int slots) {
     for (int c = 0; c <= max_region_id; ++c) if (h_first[c] != 0x7f7f7f7f) want.push_back(h_first[c]);
     std::vector<int> roots(want.size());
     if (!want.empty()) {
-      if (tmp_cap < want.size()) {
-        if (d_tmp_ids) cudaFree(d_tmp_ids);
-        if (d_tmp_info) cudaFree(d_tmp_info);
-        tmp_cap = want.size() * 2 + 1024;
-        ENG_CUDA(cudaMalloc(&d_tmp_ids, tmp_cap * 2 * sizeof(int)));
-        ENG_CUDA(cudaMalloc(&d_tmp_info, tmp_cap * sizeof(RegionRec)));
-      }
+      ENG_RC(ensure_tmp_capacity(want.size()));
       ENG_CUDA(cudaMemcpyAsync(d_tmp_ids, want.data(), sizeof(int) * want.size(), cudaMemcpyHostToDevice, stream));
       gather_i32_kernel<<<(unsigned)((want.size() + 255) / 256), 256, 0, stream>>>(d_tmp_ids, (int)want.size(), d_labels, d_tmp_ids + tmp_cap);
       ENG_CUDA(cudaMemcpyAsync(roots.data(), d_tmp_ids + tmp_cap, sizeof(int) * want.size(), cudaMemcpyDeviceToHost, stream));
@@ -487,13 +500,7 @@ int vsb200_dense::merge_constrained_regions(int slots) {
   }
   const int m = (int)ids.size();
   if (m == 0) return 0;
-  if (tmp_cap < (size_t)m) {
-    if (d_tmp_ids) cudaFree(d_tmp_ids);
-    if (d_tmp_info) cudaFree(d_tmp_info);
-    tmp_cap = (size_t)m * 2 + 1024;
-    ENG_CUDA(cudaMalloc(&d_tmp_ids, tmp_cap * 2 * sizeof(int)));
-    ENG_CUDA(cudaMalloc(&d_tmp_info, tmp_cap * sizeof(RegionRec)));
-  }
+  ENG_RC(ensure_tmp_capacity((size_t)m));
   RegionRec* d_recs = (RegionRec*)d_tmp_info;
   ENG_CUDA(cudaMemcpyAsync(d_tmp_ids, ids.data(), sizeof(int) * m, cudaMemcpyHostToDevice, stream));
   gather_rec_kernel<<<(m + 255) / 256, 256, 0, stream>>>(d_tmp_ids, m, d_rec, d_recs);
@@ -669,8 +676,10 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   const double t_dbg0 = now_ms();
   if (n_runs > runs_cap) {
     if (d_runs) cudaFree(d_runs);
-    runs_cap = (size_t)n_runs + n_runs / 2 + 1024;
-    ENG_CUDA(cudaMalloc(&d_runs, runs_cap * sizeof(RunRec)));
+    d_runs = nullptr; runs_cap = 0;
+    const size_t cap = (size_t)n_runs + n_runs / 2 + 1024;
+    ENG_CUDA(cudaMalloc(&d_runs, cap * sizeof(RunRec)));
+    runs_cap = cap;
   }
   ENG_RC(launch_rle_write(d_idimg, w, h, d_slice_ids, ns, d_row_offsets, d_runs, stream));
   // ---------------- K11 + K10 on the device (shape.cu): components of every region in every frame, their moments ----------------
@@ -734,13 +743,7 @@ int vsb200_dense::segment_and_output(bool flush_all, std::vector<std::unique_ptr
   // sizes / constraints of the representatives (GetCreateRegionInformation + size_adjust_map)
   {
     const int m = (int)regions.size();
-    if (tmp_cap < (size_t)m) {
-      if (d_tmp_ids) cudaFree(d_tmp_ids);
-      if (d_tmp_info) cudaFree(d_tmp_info);
-      tmp_cap = (size_t)m * 2 + 1024;
-      ENG_CUDA(cudaMalloc(&d_tmp_ids, tmp_cap * 2 * sizeof(int)));
-      ENG_CUDA(cudaMalloc(&d_tmp_info, tmp_cap * sizeof(RegionRec)));
-    }
+    ENG_RC(ensure_tmp_capacity((size_t)m));
     std::vector<int> ids(m);
     for (int i = 0; i < m; ++i) ids[i] = regions[i]->label;
     std::vector<int2> info(m);
