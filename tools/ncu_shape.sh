@@ -7,7 +7,7 @@ NCU="ncu --clock-control none"
 export PROFILE_REGION=0
 $NCU --metrics gpu__time_duration.sum -k 'regex:run_cc|radix|group_|result_keys|relabel_groups|scan_u32|rle_|n4_|flatten|neighbor|gather_' \
     --csv --log-file gpurun_out/ncu/r02_shape_launches.csv python tools/profile_workload.py 1920 1080 22 > gpurun_out/ncu/shape_launches.log 2>&1
-for k in run_cc_link_kernel run_cc_name_kernel radix_hist_kernel radix_scatter_kernel group_heads_count_kernel group_runs_kernel result_keys_kernel; do
+for k in run_cc_link_kernel run_cc_name_kernel radix_hist_kernel radix_scatter_kernel group_heads_count_kernel group_heads_write_kernel group_runs_kernel result_keys_kernel; do
   timeout 300 $NCU --set full --import-source on -k regex:^$k -c 1 -f -o gpurun_out/ncu/r02_$k \
       python tools/profile_workload.py 1920 1080 22 > gpurun_out/ncu/$k.log 2>&1
 done
