@@ -35,6 +35,13 @@ def test_no_cpu_fallback_without_gpu():
     assert b"no CPU fallback" in lib().vsb200_last_error()
     with pytest.raises(RuntimeError):
         u.process_frame(np.zeros((48, 64, 3), np.uint8))
+    # the region stage and the kernel-level entries refuse as well
+    from video_segment_b200.unit import RegionSegmentationUnit
+    assert not RegionSegmentationUnit().open_streams(64, 48)
+    import ctypes as C
+    n = C.c_int(-1)
+    rc = lib().vsb200_label_components(None, 64, 48, 1, None, None, 0, C.byref(n), None)
+    assert rc != 0 and n.value == -1
 
 
 def test_product_never_imports_oracle():
